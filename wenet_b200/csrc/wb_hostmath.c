@@ -1,0 +1,48 @@
+/*
+ * wb_hostmath.c -- host build of the scalar helpers in wb_math.h / wb_phi0.h so
+ * the CPU-only unit tests (tests/test_hostmath.py) can compare them with glibc,
+ * real x87 long double arithmetic and the compiled reference.  Not part of the
+ * product library; built by wenet_b200/csrc/Makefile as libwb_hostmath.so with
+ * -ffp-contract=off.
+ */
+#include "wb_math.h"
+#include "wb_phi0.h"
+
+void wbh_atan2f(const float *y, const float *x, float *out, long n)
+{
+    long i;
+    for (i = 0; i < n; i++) out[i] = wb_atan2f(y[i], x[i]);
+}
+
+void wbh_esn0_from_var(const double *v, double *out, long n)
+{
+    long i;
+    for (i = 0; i < n; i++) out[i] = wb_esn0_from_var(v[i]);
+}
+
+void wbh_llr_scale(const double *c, const float *sd, float *out, long n)
+{
+    long i;
+    for (i = 0; i < n; i++) out[i] = wb_llr_scale(c[i], sd[i]);
+}
+
+/* the same expressions in genuine x87 long double, as gcc compiles the reference */
+void wbh_esn0_from_var_x87(const double *v, double *out, long n)
+{
+    long i;
+    for (i = 0; i < n; i++) out[i] = 1.0 / (2.0L * v[i] + 1E-3);
+}
+
+void wbh_llr_scale_x87(const double *c, const float *sd, float *out, long n)
+{
+    long i;
+    for (i = 0; i < n; i++) { double s = sd[i]; out[i] = (float)((long double)c[i] * s); }
+}
+
+void wbh_phi0(const float *x, float *out, long n)
+{
+    long i;
+    wb_phi0_lut lut;
+    wb_phi0_build(&lut);
+    for (i = 0; i < n; i++) out[i] = wb_phi0_eval(&lut, x[i]);
+}

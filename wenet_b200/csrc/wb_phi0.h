@@ -1,0 +1,91 @@
+/*
+ * wb_phi0.h -- the phi0 nonlinearity of the sum-product decoder as ONE table
+ * lookup + ONE compare (reference src/phi0.c:13-218 is a Q16 compare tree).
+ *
+ * The reference maps the float argument to q = (int32_t)(x*65536) (x86
+ * cvttss2si: INT32_MIN on NaN/overflow) and returns a step function of q with
+ * 103 steps (wb_phi0_brk / wb_phi0_val in wb_tables.h, measured from the
+ * compiled reference).  Here the argument's own float bits select a bucket:
+ *
+ *     b = clamp((bits >> 17) - (113 << 6), 0, 1152)   exponent + 6 mantissa bits
+ *
+ * i.e. 64 buckets per octave over [2^-14, 16).  Every bucket holds at most one
+ * breakpoint (checked when the table is built), so
+ *
+ *     phi0(x) = (x < thr[b]) ? vlo[b] : vhi[b]
+ *
+ * is exact for every float:  x < 2^-14 (and all negatives / -NaN) clamp to
+ * bucket 0 (10.0); bucket 1152 is x >= 16: 0.0 below 32768, 10.0 from 32768 up
+ * (the cvttss2si overflow quirk) and for NaN (the compare is false).
+ * tests/test_hostmath.py sweeps every breakpoint neighbourhood and 1e7 random
+ * floats against the compiled reference.
+ */
+#ifndef WB_PHI0_H
+#define WB_PHI0_H
+
+#include "wb_math.h"
+#include "wb_tables.h"
+
+#define WB_PHI0_EXP0 113                 /* biased exponent of 2^-14 */
+#define WB_PHI0_NBUCKET (18 * 64)        /* [2^-14, 2^4) */
+#define WB_PHI0_NENTRY (WB_PHI0_NBUCKET + 1)
+
+typedef struct { float thr, vlo, vhi, pad; } wb_phi0_entry;
+typedef struct { wb_phi0_entry e[WB_PHI0_NENTRY]; } wb_phi0_lut;
+
+/* value of the reference step function at Q16 integer q >= 0 */
+static inline float wb_phi0_step(int64_t q)
+{
+    int s = 0, k;
+    for (k = 0; k < WB_PHI0_NSTEPS; k++) if ((int64_t)wb_phi0_brk[k] <= q) s = k;
+    return wb_phi0_val[s];
+}
+
+/* returns 0 on success, -1 if some bucket would need two thresholds */
+static inline int wb_phi0_build(wb_phi0_lut *lut)
+{
+    int b, k;
+    for (b = 0; b < WB_PHI0_NBUCKET; b++) {
+        int E = -14 + b / 64, j = b % 64;
+        /* bucket [xs, xe) with xs = (64+j) * 2^(E-6); in Q16 scaled by a further 2^20 (always integral) */
+        int64_t qs36 = ((int64_t)(64 + j)) << (E + 30);
+        int64_t qe36 = ((int64_t)(64 + j + 1)) << (E + 30);
+        int64_t q_first, q_last;
+        int nb = 0;
+        wb_phi0_entry en;
+        q_first = qs36 >> 20;                         /* trunc(xs * 65536) */
+        q_last = (qe36 - 1) >> 20;                    /* largest q reached inside the bucket */
+        en.thr = 0.0f; en.pad = 0.0f;
+        en.vlo = en.vhi = wb_phi0_step(q_first);
+        for (k = 0; k < WB_PHI0_NSTEPS; k++) {
+            int64_t B = wb_phi0_brk[k];
+            if (B > q_first && B <= q_last) {
+                nb++;
+                en.thr = (float)((double)B / 65536.0);   /* exact */
+                en.vhi = wb_phi0_val[k];
+            }
+        }
+        if (nb > 1) return -1;
+        lut->e[b] = en;
+    }
+    lut->e[WB_PHI0_NBUCKET].thr = 32768.0f;
+    lut->e[WB_PHI0_NBUCKET].vlo = 0.0f;
+    lut->e[WB_PHI0_NBUCKET].vhi = 10.0f;
+    lut->e[WB_PHI0_NBUCKET].pad = 0.0f;
+    return 0;
+}
+
+WB_HD int wb_phi0_bucket(float x)
+{
+    int b = ((int32_t)wb_f2u(x) >> 17) - (WB_PHI0_EXP0 << 6);
+    b = b < 0 ? 0 : b;
+    return b > WB_PHI0_NBUCKET ? WB_PHI0_NBUCKET : b;
+}
+
+WB_HD float wb_phi0_eval(const wb_phi0_lut *lut, float x)
+{
+    wb_phi0_entry en = lut->e[wb_phi0_bucket(x)];
+    return (x < en.thr) ? en.vlo : en.vhi;
+}
+
+#endif /* WB_PHI0_H */
