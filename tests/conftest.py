@@ -1,0 +1,27 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle_port():
+    from oracle import oracle as O
+    O.build()
+    return O.Oracle("port")
+
+
+@pytest.fixture(scope="session")
+def oracle_ref():
+    from oracle import oracle as O
+    if not O.have_reference():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    return O.Oracle("reference")

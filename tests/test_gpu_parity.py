@@ -1,0 +1,247 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (wenet_b200.engine -> libwenet_b200.so),
+against the CPU oracle (oracle/liboracle.so, itself pinned to the compiled reference by
+tests/test_oracle_vs_ref.py and the committed golden vectors) on the same seeded inputs.
+
+Bars: soft decisions, LLRs, iteration counts, parity counts, nin sequence and packet bytes are all
+BIT-EXACT (the north-star tolerance for LLRs is 1e-4 relative; we hold them to zero difference).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from wenet_b200 import siggen
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NCODE = 2580
+
+
+@pytest.fixture(scope="module")
+def eng_mod():
+    from wenet_b200 import engine
+    return engine
+
+
+def _noisy_codewords(oracle, n, snr_db_list, seed):
+    """random valid codewords -> BPSK + AWGN soft decisions -> sd_to_llr (oracle) -> LLR rows"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for k in range(n):
+        data = rng.integers(0, 2, 2064, dtype=np.uint8)
+        if k % 7 == 3:
+            data[:] = 0                       # the all-zero-data early exit of run_ldpc_decoder
+        par = oracle.ldpc_encode(data)
+        cw = np.concatenate([data, par]).astype(np.float64)
+        snr = snr_db_list[k % len(snr_db_list)]
+        sigma = 10.0 ** (-snr / 20.0)
+        sd = (1.0 - 2.0 * cw) * rng.uniform(0.3, 3.0) + sigma * rng.standard_normal(NCODE)
+        out.append(oracle.sd_to_llr(sd.astype(np.float32).astype(np.float64)))
+    return np.stack(out)
+
+
+def test_ldpc_known_answer(eng_mod):
+    """reference src/H2064_516_sparse.h:27-33: input[] decodes to detected_data[] in 8 iterations"""
+    z = np.load(os.path.join(GOLD, "ldpc_kat.npz"))
+    e = eng_mod.Engine(1, framing="v1", chunk_samples=4096)
+    bits, iters, pcc = e.ldpc_decode_batch(z["llr"][None, :], max_iter=int(z["max_iter"]))
+    assert iters[0] == int(z["iters"]) == 8
+    assert pcc[0] == int(z["parity_ok"]) == 516
+    assert np.array_equal(bits[0], z["detected"].astype(np.uint8))
+    e.close()
+
+
+@pytest.mark.parametrize("max_iter", [10, 100])
+def test_ldpc_random_vs_oracle(eng_mod, oracle_port, max_iter):
+    n = 96 if max_iter == 10 else 24
+    llr = _noisy_codewords(oracle_port, n, [1.0, 2.0, 3.0, 4.0, 6.0, 9.0], seed=7 + max_iter)
+    llr[5, 100] = np.float32(40000.0)         # phi0 overflow quirk (x >= 32768 -> 10.0)
+    llr[6, 7] = np.float32(0.0)
+    e = eng_mod.Engine(1, framing="v1", chunk_samples=4096)
+    bits, iters, pcc = e.ldpc_decode_batch(llr, max_iter=max_iter)
+    e.close()
+    for k in range(n):
+        b, it, pc = oracle_port.ldpc_decode(llr[k], max_iter=max_iter, pcc_init=-1)
+        assert it == iters[k], (k, it, iters[k])
+        assert pc == pcc[k], (k, pc, pcc[k])
+        assert np.array_equal(b, bits[k]), k
+    assert len(set(iters.tolist())) > 2       # the sweep really exercises different iteration counts
+
+
+def test_sd_to_llr_vs_oracle(eng_mod, oracle_port):
+    rng = np.random.default_rng(11)
+    sd = (rng.choice([-1.0, 1.0], size=(40, NCODE)) * rng.uniform(0.1, 30.0, size=(40, 1))
+          + rng.standard_normal((40, NCODE)) * rng.uniform(0.01, 2.0, size=(40, 1))).astype(np.float32)
+    sd[3, :50] = 0.0
+    sd[4] *= 1e-6
+    e = eng_mod.Engine(1, framing="v1", chunk_samples=4096)
+    llr = e.sd_to_llr_batch(sd)
+    e.close()
+    for k in range(sd.shape[0]):
+        ref = oracle_port.sd_to_llr(sd[k].astype(np.float64))
+        assert np.array_equal(ref.view(np.uint32), llr[k].view(np.uint32)), k
+
+
+def _run_oracle_stream(oracle, raw, fmt, Fs, Rs, M, framing, max_iter=10, P=None):
+    f = oracle.fsk(Fs, Rs, M=M, P=P)
+    sd, log, consumed = f.run(raw, fmt)
+    res = None
+    if framing:
+        res = oracle.deframer(framing, max_iter).feed(sd)
+    return sd, log, consumed, res
+
+
+STREAM_CASES = [
+    # (id, fmt, ebno, ppm, n_packets)
+    ("cf32_10dB", "cf32", 10.0, 0.0, 3),
+    ("cf32_8dB_ppm", "cf32", 8.0, 2500.0, 3),
+    ("cs16_9dB_negppm", "cs16", 9.0, -3000.0, 2),
+    ("cu8_12dB", "cu8", 12.0, 0.0, 2),
+    ("cf32_5dB", "cf32", 5.0, 0.0, 2),
+]
+
+
+@pytest.mark.parametrize("case", STREAM_CASES, ids=[c[0] for c in STREAM_CASES])
+def test_stream_v1_vs_oracle(eng_mod, oracle_port, case):
+    """FSK soft decisions, nin sequence, LLRs, iterations and packets of one v1 stream, one chunk"""
+    _, fmt, ebno, ppm, npk = case
+    raw, payloads = siggen.make_stream(3, n_packets=npk, ebno_db=ebno, fmt=fmt, clock_ppm=ppm)
+    cfg = siggen.V1
+    sd_o, log_o, cons_o, res_o = _run_oracle_stream(oracle_port, raw, fmt, cfg["Fs"], cfg["Rs"], 2, "v1")
+    nsamp = raw.size // eng_mod.FMT_ELEMS[fmt]
+    e = eng_mod.Engine(1, Fs=cfg["Fs"], Rs=cfg["Rs"], in_fmt=fmt, framing="v1", chunk_samples=nsamp + 1024, keep_llr=True)
+    e.enable_frame_log(len(log_o) + 4)
+    e.feed([raw])
+    e.process()
+    e.sync()
+    sd_g = e.drain_soft(0)
+    assert e.last_samples == cons_o
+    assert sd_g.size == sd_o.size
+    log_g = e.read_frame_log(0, len(log_o))
+    assert np.array_equal(log_g[:, 0], log_o[:, 0]), "nin sequence"
+    binw = np.float32(cfg["Fs"]) / np.float32(256)
+    assert np.array_equal(log_g[:, 1] * binw, log_o[:, 1]) and np.array_equal(log_g[:, 2] * binw, log_o[:, 2]), "f_est"
+    assert np.array_equal(log_g[:, 5].view(np.uint32), log_o[:, 5].view(np.uint32)), "norm_rx_timing"
+    assert np.array_equal(log_g[:, 6].view(np.uint32), log_o[:, 6].view(np.uint32)), "ppm"
+    bad = np.nonzero(sd_g.view(np.uint32) != sd_o.view(np.uint32))[0]
+    assert bad.size == 0, "soft decisions differ first at %s" % bad[:5]
+    cw, llr = e.drain_codewords(with_llr=True)
+    assert len(cw) == len(res_o["iters"])
+    assert np.array_equal(llr.view(np.uint32), res_o["llr"].view(np.uint32))
+    assert np.array_equal(cw["iters"], res_o["iters"])
+    assert np.array_equal(cw["crc_ok"], res_o["crc_ok"])
+    assert np.array_equal(cw["bytes"], res_o["bytes258"])
+    pk = e.drain_packets(0)
+    assert pk == res_o["packets"]
+    if ebno >= 9.0:
+        assert pk == b"".join(payloads)
+    e.close()
+
+
+def test_stream_chunked_feed_matches_one_shot(eng_mod, oracle_port):
+    """feeding ragged chunks (state carried in HBM, half-collected packets carried over) == one pass"""
+    cfg = siggen.V1
+    raws, refs = [], []
+    for s in range(5):
+        raw, _ = siggen.make_stream(20 + s, n_packets=3, ebno_db=9.0 + s, fmt="cs16", clock_ppm=(-2000 + 1000 * s))
+        raws.append(raw)
+        refs.append(_run_oracle_stream(oracle_port, raw, "cs16", cfg["Fs"], cfg["Rs"], 2, "v1"))
+    e = eng_mod.Engine(5, Fs=cfg["Fs"], Rs=cfg["Rs"], in_fmt="cs16", framing="v1", chunk_samples=40000)
+    rng = np.random.default_rng(5)
+    pos = [0] * 5
+    sds = [[] for _ in range(5)]
+    pk = [b""] * 5
+    while any(pos[s] < raws[s].size for s in range(5)):
+        chunk = []
+        for s in range(5):
+            n = int(rng.integers(0, 30000)) * 2
+            if rng.random() < 0.15:
+                n = 0
+            chunk.append(raws[s][pos[s]:pos[s] + n])
+            pos[s] += len(chunk[-1])
+        e.feed(chunk)
+        e.process()
+        e.sync()
+        for s in range(5):
+            sds[s].append(e.drain_soft(s))
+            pk[s] += e.drain_packets(s)
+    for s in range(5):
+        sd = np.concatenate(sds[s])
+        assert np.array_equal(sd.view(np.uint32), refs[s][0].view(np.uint32)), s
+        assert pk[s] == refs[s][3]["packets"], s
+        assert len(pk[s]) == 3 * 256
+    e.close()
+
+
+def test_stream_v2_vs_oracle(eng_mod, oracle_port):
+    cfg = siggen.V2
+    raws, refs = [], []
+    for s in range(3):
+        raw, payloads = siggen.make_stream(40 + s, n_packets=2, ebno_db=9.0 + 2 * s, framing="v2", fmt="cf32",
+                                           clock_ppm=1500.0 * s)
+        raws.append(raw)
+        refs.append((_run_oracle_stream(oracle_port, raw, "cf32", cfg["Fs"], cfg["Rs"], 2, "v2"), payloads))
+    n = max(r.size for r in raws) // 2
+    e = eng_mod.Engine(3, Fs=cfg["Fs"], Rs=cfg["Rs"], in_fmt="cf32", framing="v2", chunk_samples=n + 1024, keep_llr=True)
+    e.feed(raws)
+    e.process()
+    e.sync()
+    cw, llr = e.drain_codewords(with_llr=True)
+    k = 0
+    for s in range(3):
+        (sd_o, log_o, cons_o, res_o), payloads = refs[s]
+        sd_g = e.drain_soft(s)
+        assert np.array_equal(sd_g.view(np.uint32), sd_o.view(np.uint32)), s
+        ncw = len(res_o["iters"])
+        assert np.array_equal(cw["stream"][k:k + ncw], np.full(ncw, s))
+        assert np.array_equal(llr[k:k + ncw].view(np.uint32), res_o["llr"].view(np.uint32))
+        assert np.array_equal(cw["iters"][k:k + ncw], res_o["iters"])
+        k += ncw
+        pk = e.drain_packets(s)
+        assert pk == res_o["packets"] == b"".join(payloads)
+    assert k == len(cw)
+    e.close()
+
+
+def test_4fsk_soft_vs_oracle(eng_mod, oracle_port):
+    raws, refs = [], []
+    for s in range(3):
+        raw, sym = siggen.make_4fsk_stream(60 + s, 3000, ebno_db=8.0 + 3 * s)
+        raws.append(raw)
+        refs.append(oracle_port.fsk(921416, 115177, M=4).run(raw, "cf32"))
+    e = eng_mod.Engine(3, M=4, in_fmt="cf32", framing="none", chunk_samples=raws[0].size // 2 + 1024)
+    e.feed(raws)
+    e.process()
+    e.sync()
+    for s in range(3):
+        sd_g = e.drain_soft(s)
+        assert np.array_equal(sd_g.view(np.uint32), refs[s][0].view(np.uint32)), s
+    e.close()
+
+
+def test_many_streams_one_launch(eng_mod, oracle_port):
+    """more streams than one CTA holds, ragged lengths, some empty: every stream still matches"""
+    cfg = siggen.V1
+    n = 37
+    raws = []
+    for s in range(n):
+        if s % 9 == 4:
+            raws.append(np.zeros(0, dtype=np.float32))
+            continue
+        raw, _ = siggen.make_stream(100 + s, n_samples=30000 + 997 * s, ebno_db=6.0 + (s % 7), fmt="cf32",
+                                    clock_ppm=float((s % 5 - 2) * 1500))
+        raws.append(raw)
+    e = eng_mod.Engine(n, in_fmt="cf32", framing="v1", chunk_samples=80000)
+    e.feed(raws)
+    e.process()
+    e.sync()
+    for s in range(n):
+        sd_g = e.drain_soft(s)
+        if raws[s].size == 0:
+            assert sd_g.size == 0
+            continue
+        sd_o, _, _, res_o = _run_oracle_stream(oracle_port, raws[s], "cf32", cfg["Fs"], cfg["Rs"], 2, "v1")
+        assert np.array_equal(sd_g.view(np.uint32), sd_o.view(np.uint32)), s
+        assert e.drain_packets(s) == res_o["packets"], s
+    e.close()

@@ -1,0 +1,1067 @@
+/*
+ * wb_engine.cu -- host side of libwenet_b200.so: the C ABI of include/wenet_b200.h.
+ *
+ * Owns the HBM layout described in wb_internal.h, builds the constant tables the kernels use
+ * (with the host libm, i.e. the cosf/sinf the reference itself would call), and sequences the
+ * kernels on one CUDA stream:
+ *
+ *   wb_process:  K1 wb_fsk_kernel -> K2 wb_deframe_kernel -> K3 wb_llr_stats_kernel
+ *                -> K4 wb_ldpc_kernel -> wb_carry_kernel
+ *
+ * There is NO CPU fallback: without a CUDA device wb_create fails with WB_ENODEV.
+ */
+#include <cuda_runtime.h>
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <deque>
+#include <vector>
+
+#include "wb_internal.h"
+#include "wb_math.h"
+#include "wb_phi0.h"
+#include "wb_fsk_kernel.cuh"
+#include "wb_deframe_kernel.cuh"
+#include "wb_ldpc_kernel.cuh"
+
+#define WB_HEADROOM 512u    /* samples in front of every input row for the parked remainder (>= WB_MAX_NIN) */
+
+static thread_local char g_err[512] = "";
+
+static int wb_fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return wb_fail(WB_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct wb_engine {
+    wb_config cfg;
+    wb_fsk_params fp;
+    wb_deframe_params dp;
+    int max_iter;
+    cudaStream_t stream;
+    cudaEvent_t ev[8];
+    cudaEvent_t tev0, tev1;
+    /* device buffers */
+    unsigned char *d_in;
+    unsigned long long in_stride, in_cap;          /* bytes per row; samples per row (headroom + chunk) */
+    wb_stream_state *d_state;
+    wb_cursor *d_cursor;
+    float *d_sd;
+    unsigned long long sd_stride;
+    unsigned sd_cap;
+    unsigned *d_jobs;
+    double *d_c4;
+    wb_codeword *d_cw, *d_cw_packed;
+    float *d_llr, *d_llr_packed;
+    unsigned *d_gather;
+    unsigned long long *d_fill;
+    int job_cap;
+    float *d_frame_log;
+    int log_cap;
+    /* tables */
+    void *d_tables;
+    ushort4 *d_vedge;
+    uint16_t *d_crc_tab;
+    unsigned crc0;
+    uint8_t *d_scramble;
+    wb_phi0_compact *d_lut;
+    /* resident LDPC benchmark */
+    float *d_bench_llr;
+    uint8_t *d_bench_bits;
+    int *d_bench_iters, *d_bench_pcc;
+    size_t bench_n;
+    /* host mirrors */
+    std::vector<wb_cursor> cursor;                 /* as of the last wb_sync */
+    std::vector<unsigned long long> fill;          /* samples resident per stream (host's view) */
+    std::vector<int> nin;
+    std::vector<std::deque<uint8_t>> packets;      /* CRC-valid payloads not yet drained, per stream */
+    std::vector<wb_codeword> last_cw;              /* codewords of the last wb_process, (stream, seq) order */
+    std::vector<float> last_llr;
+    bool uniform_fill;                             /* every stream has the same fill (strided feed possible) */
+    bool pending;                                  /* a wb_process has not been collected yet */
+    bool resident_mode;                            /* wb_dev_set_fill: do not compact */
+    uint64_t launches;
+    uint64_t last_codewords, last_samples;
+    float kernel_ms[4];
+    size_t fsk_smem;
+};
+
+/* ---- table construction ------------------------------------------------- */
+
+typedef struct { float r, i; } hcpx;
+static hcpx hcmul(hcpx a, hcpx b)
+{
+    hcpx c;
+    c.r = a.r * b.r - a.i * b.i;
+    c.i = a.r * b.i + a.i * b.r;
+    return c;
+}
+static hcpx hcexpj(float phi) { hcpx c; c.r = cosf(phi); c.i = sinf(phi); return c; }
+
+/* kiss_fft factorisation, reference src/kiss_fft.c:309-330 */
+static int fft_factor(int n, int *fac)
+{
+    int p = 4, cnt = 0;
+    double fs = floor(sqrt((double)n));
+    do {
+        while (n % p) {
+            if (p == 4) p = 2; else if (p == 2) p = 3; else p += 2;
+            if (p > fs) p = n;
+        }
+        n /= p;
+        fac[2 * cnt] = p; fac[2 * cnt + 1] = n; cnt++;
+    } while (n > 1);
+    return cnt;
+}
+
+static void fft_perm(uint16_t *perm, int out_base, int in_base, int fstride, const int *fac)
+{
+    int p = fac[0], m = fac[1], k;
+    if (m == 1) {
+        for (k = 0; k < p; k++) perm[out_base + k] = (uint16_t)(in_base + k * fstride);
+    } else {
+        for (k = 0; k < p; k++) fft_perm(perm, out_base + k * m, in_base + k * fstride, fstride * p, fac + 2);
+    }
+}
+
+static uint16_t crc16_ccitt(const uint8_t *d, int n, uint16_t crc)
+{
+    for (int i = 0; i < n; i++) {
+        crc ^= (uint16_t)(d[i] << 8);
+        for (int b = 0; b < 8; b++) crc = (crc & 0x8000) ? (uint16_t)((crc << 1) ^ 0x1021) : (uint16_t)(crc << 1);
+    }
+    return crc;
+}
+
+static int build_fsk_params(const wb_config *cfg, wb_fsk_params *fp)
+{
+    int Fs = cfg->Fs, Rs = cfg->Rs, M = cfg->M, P = cfg->P;
+    memset(fp, 0, sizeof(*fp));
+    if (Fs <= 0 || Rs <= 0 || Rs > Fs) return wb_fail(WB_EINVAL, "invalid Fs/Rs");
+    if (!(M == 2 || M == 4)) return wb_fail(WB_EINVAL, "M must be 2 or 4");
+    if (Fs % Rs) return wb_fail(WB_EINVAL, "Fs must be an integer multiple of Rs (reference src/fsk.c:137)");
+    if (P <= 0) P = Fs / Rs;                                   /* reference src/fsk_demod.c:186-188 */
+    int Ts = Fs / Rs;
+    if (Ts % P) return wb_fail(WB_EINVAL, "Fs/Rs must be a multiple of P (reference src/fsk.c:139)");
+    if (Ts > WB_MAX_TS || Ts < 4) return wb_fail(WB_EINVAL, "Fs/Rs = %d unsupported (4..%d samples per symbol)", Ts, WB_MAX_TS);
+    fp->Fs = Fs; fp->Rs = Rs; fp->Ts = Ts; fp->P = P; fp->M = M;
+    fp->Nsym = WB_FRAME_SYMS;
+    fp->N = Ts * fp->Nsym;
+    fp->Nmem = fp->N + 2 * Ts;
+    fp->Nbits = (M == 2) ? fp->Nsym : 2 * fp->Nsym;
+    int Ndft = 0;
+    for (int i = 1; i > 0 && i <= fp->N; i <<= 1) if (fp->N & i) Ndft = i;   /* reference src/fsk.c:169-173 */
+    fp->Ndft = Ndft;
+    fp->nstash = 4 * Ts;
+    fp->step = Ts / P;
+    fp->nint = (fp->Nsym + 1) * P;
+    fp->nsteps = fp->Nmem - fp->step;
+    fp->nmax = fp->N + Ts / 2;
+    if (Ndft > WB_MAX_NDFT || Ndft < 64) return wb_fail(WB_EINVAL, "Ndft = %d unsupported", Ndft);
+    if (fp->N - Ts / 2 < Ndft || fp->nmax >= 2 * Ndft || fp->nmax > WB_MAX_NIN)
+        return wb_fail(WB_EINVAL, "frame length %d vs Ndft %d unsupported (needs exactly one estimator FFT per frame)", fp->N, Ndft);
+    if (Fs / Ndft < 1) return wb_fail(WB_EINVAL, "Fs too low");
+    int est_min = Rs / 4, est_max = Fs / 2 - Rs / 4, est_space = Rs - Rs / 5;   /* reference src/fsk.c:175-180 */
+    if (cfg->est_lo > 0 || cfg->est_hi > 0) {                  /* fsk_set_est_limits, reference src/fsk.c:522-535 */
+        est_min = cfg->est_lo < 0 ? 0 : cfg->est_lo;
+        est_max = cfg->est_hi;
+    }
+    fp->f_min = (int)(((long long)est_min * Ndft) / Fs);
+    fp->f_max = (int)(((long long)est_max * Ndft) / Fs);
+    fp->f_zero = (int)(((long long)est_space * Ndft) / Fs);
+    fp->tc = (float)(0.95 * Ndft / Fs);
+    fp->in_fmt = cfg->in_fmt;
+    switch (cfg->in_fmt) {
+    case WB_FMT_CF32: fp->in_bps = 8; break;
+    case WB_FMT_CS16: fp->in_bps = 4; break;
+    case WB_FMT_CU8: case WB_FMT_S16: fp->in_bps = 2; break;
+    default: return wb_fail(WB_EINVAL, "unknown in_fmt %d", cfg->in_fmt);
+    }
+    fp->xlen = (fp->nstash + fp->nmax + 1) & ~1;
+    fp->blen = std::max((M - 1) * fp->nint, Ndft);
+    int bytes = (fp->xlen + fp->blen) * 8;
+    fp->sreg = ((bytes + 127 - 8) / 128) * 128 + 8;            /* == 8 (mod 128), >= bytes */
+    if (fp->sreg < bytes) fp->sreg += 128;
+    return WB_OK;
+}
+
+static int upload_tables(wb_engine *e)
+{
+    wb_fsk_params &fp = e->fp;
+    const int Ndft = fp.Ndft, nh = Ndft / 2;
+    /* one allocation, 256-byte aligned sections */
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    size_t o_hann = take(sizeof(float) * Ndft), o_tw = take(sizeof(float2) * Ndft), o_perm = take(sizeof(uint16_t) * Ndft);
+    size_t o_pft = take(sizeof(float2) * fp.nint), o_dphi = take(sizeof(float2) * nh), o_back = take(sizeof(float2) * 3 * nh);
+    std::vector<unsigned char> h(off, 0);
+    float *hann = (float *)&h[o_hann];
+    hcpx *tw = (hcpx *)&h[o_tw], *pft = (hcpx *)&h[o_pft], *dphi = (hcpx *)&h[o_dphi], *back = (hcpx *)&h[o_back];
+    uint16_t *perm = (uint16_t *)&h[o_perm];
+    /* Hann table by oscillator recurrence, reference src/fsk.c:94-111 */
+    {
+        hcpx d = hcexpj((float)((2 * M_PI) / ((float)Ndft - 1)));
+        hcpx r; r.r = .5f; r.i = 0;
+        hcpx dc = d; dc.i = -dc.i;
+        r = hcmul(dc, r);
+        for (int i = 0; i < Ndft; i++) { r = hcmul(d, r); hann[i] = (float)(.5 - r.r); }
+    }
+    /* kiss_fft twiddles, reference src/kiss_fft.c:357-363 */
+    for (int i = 0; i < Ndft; i++) {
+        const double pi = 3.141592653589793238462643383279502884197169399375105820974944;
+        double phase = -2 * pi * i / Ndft;
+        tw[i].r = cosf((float)phase); tw[i].i = sinf((float)phase);
+    }
+    int fac[64];
+    int nl = fft_factor(Ndft, fac);
+    if (nl > WB_MAX_LEVELS) return wb_fail(WB_EINVAL, "FFT too deep");
+    for (int l = 0; l < nl; l++) if (fac[2 * l] != 4 && fac[2 * l] != 2) return wb_fail(WB_EINVAL, "unsupported FFT radix");
+    fft_perm(perm, 0, 0, 1, fac);
+    fp.n_levels = nl;
+    {
+        int fstride = 1;
+        for (int l = 0; l < nl; l++) {             /* top level first in fac[], leaf first in lev_* */
+            int dst = nl - 1 - l;
+            fp.lev_p[dst] = fac[2 * l]; fp.lev_m[dst] = fac[2 * l + 1]; fp.lev_fstride[dst] = fstride;
+            fstride *= fac[2 * l];
+        }
+    }
+    /* fine-timing oscillator, reference src/fsk.c:858-873 */
+    {
+        hcpx d = hcexpj((float)(2 * M_PI * ((float)fp.Rs / (float)(fp.P * fp.Rs))));
+        hcpx ph; ph.r = 1; ph.i = 0;
+        for (int i = 0; i < fp.nint; i++) { pft[i] = ph; ph = hcmul(ph, d); }
+    }
+    /* per-bin tone oscillators, reference src/fsk.c:756-764, :671 */
+    for (int b = 0; b < nh; b++) {
+        float f = (float)b * ((float)fp.Fs / (float)Ndft);
+        dphi[b] = hcexpj((float)(2 * M_PI * ((f) / (float)fp.Fs)));
+        for (int k = 0; k < 3; k++) {
+            int nin = fp.N + (k - 1) * (fp.Ts / 2);
+            back[k * nh + b] = hcexpj((float)(-2 * (fp.Nmem - nin - fp.step) * M_PI * ((f) / (float)fp.Fs)));
+        }
+    }
+    if (cudaMalloc(&e->d_tables, off) != cudaSuccess) return wb_fail(WB_ENOMEM, "cudaMalloc tables");
+    CU(cudaMemcpy(e->d_tables, h.data(), off, cudaMemcpyHostToDevice));
+    unsigned char *base = (unsigned char *)e->d_tables;
+    fp.hann = (const float *)(base + o_hann); fp.tw = (const float2 *)(base + o_tw);
+    fp.perm = (const uint16_t *)(base + o_perm); fp.pft = (const float2 *)(base + o_pft);
+    fp.dphi = (const float2 *)(base + o_dphi); fp.back = (const float2 *)(base + o_back);
+
+    /* LDPC edge table: message word of (data column i, k-th check in H_cols order) */
+    std::vector<ushort4> vedge(WB_NDATA);
+    for (int i = 0; i < WB_NDATA; i++) {
+        unsigned short w[3];
+        for (int k = 0; k < WB_COLW; k++) {
+            int c = wb_hcols[i * WB_COLW + k], found = -1;
+            for (int t = 0; t < WB_ROWW; t++) if (wb_hrows[c * WB_ROWW + t] == i) { found = t; break; }
+            if (found < 0) return wb_fail(WB_EINVAL, "H tables inconsistent");
+            w[k] = (unsigned short)(found * WB_NPAR + c);
+        }
+        vedge[i] = make_ushort4(w[0], w[1], w[2], 0);
+    }
+    CU(cudaMalloc(&e->d_vedge, sizeof(ushort4) * WB_NDATA));
+    CU(cudaMemcpy(e->d_vedge, vedge.data(), sizeof(ushort4) * WB_NDATA, cudaMemcpyHostToDevice));
+    /* CRC as an affine map: crc(msg) = crc(0..0) ^ XOR_{set bits} T[bit] */
+    std::vector<uint16_t> crc_tab(2048);
+    {
+        uint8_t msg[256];
+        memset(msg, 0, sizeof(msg));
+        e->crc0 = crc16_ccitt(msg, 256, 0xFFFF);
+        for (int i = 0; i < 2048; i++) {
+            msg[i >> 3] = (uint8_t)(0x80u >> (i & 7));
+            crc_tab[i] = crc16_ccitt(msg, 256, 0x0000);
+            msg[i >> 3] = 0;
+        }
+    }
+    CU(cudaMalloc(&e->d_crc_tab, sizeof(uint16_t) * 2048));
+    CU(cudaMemcpy(e->d_crc_tab, crc_tab.data(), sizeof(uint16_t) * 2048, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&e->d_scramble, WB_SCRAMBLE_LEN));
+    CU(cudaMemcpy(e->d_scramble, wb_scramble_neg, WB_SCRAMBLE_LEN, cudaMemcpyHostToDevice));
+    static wb_phi0_compact lut;
+    if (wb_phi0_build_compact(&lut) != 0) return wb_fail(WB_EINVAL, "phi0 table: two breakpoints in one bucket");
+    CU(cudaMalloc(&e->d_lut, sizeof(lut)));
+    CU(cudaMemcpy(e->d_lut, &lut, sizeof(lut), cudaMemcpyHostToDevice));
+    return WB_OK;
+}
+
+/* ---- lifecycle ---------------------------------------------------------- */
+
+extern "C" int wb_abi_version(void) { return WB_ABI_VERSION; }
+extern "C" const char *wb_last_error(void) { return g_err; }
+
+extern "C" void wb_destroy(wb_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->d_in); cudaFree(e->d_state); cudaFree(e->d_cursor); cudaFree(e->d_sd); cudaFree(e->d_jobs);
+    cudaFree(e->d_c4); cudaFree(e->d_cw); cudaFree(e->d_cw_packed); cudaFree(e->d_llr); cudaFree(e->d_llr_packed);
+    cudaFree(e->d_gather); cudaFree(e->d_fill); cudaFree(e->d_frame_log); cudaFree(e->d_tables); cudaFree(e->d_vedge);
+    cudaFree(e->d_crc_tab); cudaFree(e->d_scramble); cudaFree(e->d_lut);
+    cudaFree(e->d_bench_llr); cudaFree(e->d_bench_bits); cudaFree(e->d_bench_iters); cudaFree(e->d_bench_pcc);
+    for (int i = 0; i < 8; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    if (e->tev0) cudaEventDestroy(e->tev0);
+    if (e->tev1) cudaEventDestroy(e->tev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+static int init_states(wb_engine *e)
+{
+    const int n = e->cfg.n_streams;
+    std::vector<wb_stream_state> h(n);
+    memset(h.data(), 0, sizeof(wb_stream_state) * n);
+    for (int s = 0; s < n; s++) {
+        for (int m = 0; m < WB_MAXM; m++) { h[s].phi_c[m].x = 1.0f; h[s].phi_c[m].y = 0.0f; }   /* comp_exp_j(0) */
+        h[s].nin = e->fp.N;
+        h[s].in_pos = h[s].in_fill = WB_HEADROOM;
+    }
+    CU(cudaMemcpy(e->d_state, h.data(), sizeof(wb_stream_state) * n, cudaMemcpyHostToDevice));
+    CU(cudaMemset(e->d_cursor, 0, sizeof(wb_cursor) * n));
+    for (int s = 0; s < n; s++) {
+        memset(&e->cursor[s], 0, sizeof(wb_cursor));
+        e->cursor[s].nin = e->fp.N;
+        e->fill[s] = 0;
+        e->nin[s] = e->fp.N;
+        e->packets[s].clear();
+    }
+    e->uniform_fill = true;
+    e->pending = false;
+    e->resident_mode = false;
+    return WB_OK;
+}
+
+template <int M, int TS>
+static cudaError_t fsk_set_attr(size_t smem)
+{
+    return cudaFuncSetAttribute(wb_fsk_kernel<M, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+extern "C" int wb_create(const wb_config *cfg, wb_engine **out)
+{
+    if (!cfg || !out) return wb_fail(WB_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(wb_config)) return wb_fail(WB_EINVAL, "wb_config.struct_size mismatch (ABI %d)", WB_ABI_VERSION);
+    if (cfg->n_streams <= 0 || cfg->n_streams > 65535 * 16) return wb_fail(WB_EINVAL, "n_streams out of range");
+    if (cfg->framing < WB_FRAMING_NONE || cfg->framing > WB_FRAMING_V2) return wb_fail(WB_EINVAL, "unknown framing");
+    if (cfg->framing != WB_FRAMING_NONE && cfg->M != 2) return wb_fail(WB_EINVAL, "framing needs 2-FSK (the reference has no 4-FSK deframer)");
+    if (cfg->chunk_samples < 1024) return wb_fail(WB_EINVAL, "chunk_samples too small");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return wb_fail(WB_ENODEV, "no CUDA device visible: libwenet_b200 has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return wb_fail(WB_EINVAL, "device %d of %d", cfg->device, ndev);
+    CU(cudaSetDevice(cfg->device));
+
+    wb_engine *e = new wb_engine();
+    memset(&e->cfg, 0, sizeof(e->cfg));
+    e->cfg = *cfg;
+    e->stream = nullptr; e->tev0 = e->tev1 = nullptr;
+    for (int i = 0; i < 8; i++) e->ev[i] = nullptr;
+    e->d_in = nullptr; e->d_state = nullptr; e->d_cursor = nullptr; e->d_sd = nullptr; e->d_jobs = nullptr; e->d_c4 = nullptr;
+    e->d_cw = e->d_cw_packed = nullptr; e->d_llr = e->d_llr_packed = nullptr; e->d_gather = nullptr; e->d_fill = nullptr; e->d_frame_log = nullptr;
+    e->d_tables = nullptr; e->d_vedge = nullptr; e->d_crc_tab = nullptr; e->d_scramble = nullptr; e->d_lut = nullptr;
+    e->d_bench_llr = nullptr; e->d_bench_bits = nullptr; e->d_bench_iters = e->d_bench_pcc = nullptr; e->bench_n = 0;
+    e->launches = 0; e->last_codewords = e->last_samples = 0; e->log_cap = 0;
+    memset(e->kernel_ms, 0, sizeof(e->kernel_ms));
+    int rc = build_fsk_params(cfg, &e->fp);
+    if (rc) { delete e; return rc; }
+    e->cfg.P = e->fp.P;
+    e->max_iter = cfg->ldpc_max_iter > 0 ? cfg->ldpc_max_iter : WB_LDPC_MAX_ITER;
+    /* deframer constants: reference src/drs232_ldpc.c:65-86 / src/wenet_ldpc.c:65-82 */
+    {
+        static const uint8_t uwb[4] = {0xAB, 0xCD, 0xEF, 0x01};
+        uint8_t uw[40]; int nb = 0;
+        wb_deframe_params &dp = e->dp;
+        memset(&dp, 0, sizeof(dp));
+        dp.mode = cfg->framing;
+        if (cfg->framing == WB_FRAMING_V2) {
+            for (int b = 0; b < 4; b++) for (int k = 7; k >= 0; k--) uw[nb++] = (uwb[b] >> k) & 1;
+            dp.uw_thresh = 28; dp.nsym = WB_PKT_BODY_BYTES * 8;
+        } else {
+            for (int b = 0; b < 4; b++) { uw[nb++] = 0; for (int k = 0; k < 8; k++) uw[nb++] = (uwb[b] >> k) & 1; uw[nb++] = 1; }
+            dp.uw_thresh = 35; dp.nsym = WB_PKT_BODY_BYTES * 10;
+        }
+        dp.uw_bits = nb;
+        dp.uw = 0;
+        for (int i = 0; i < nb; i++) dp.uw |= (unsigned long long)uw[i] << (nb - 1 - i);   /* oldest bit highest */
+        dp.uw_mask = (nb == 64) ? ~0ULL : ((1ULL << nb) - 1);
+    }
+    const int n = cfg->n_streams;
+    e->cursor.resize(n); e->fill.resize(n); e->nin.resize(n); e->packets.resize(n);
+
+#define CRE(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+        wb_fail(e_ == cudaErrorMemoryAllocation ? WB_ENOMEM : WB_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+        wb_destroy(e); return e_ == cudaErrorMemoryAllocation ? WB_ENOMEM : WB_ECUDA; } } while (0)
+
+    CRE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) CRE(cudaEventCreate(&e->ev[i]));
+    CRE(cudaEventCreate(&e->tev0)); CRE(cudaEventCreate(&e->tev1));
+    e->in_cap = WB_HEADROOM + cfg->chunk_samples;
+    e->in_stride = ((e->in_cap * e->fp.in_bps + 64) + 255) & ~255ULL;
+    unsigned long long max_frames = e->in_cap / (unsigned)(e->fp.N - e->fp.Ts / 2) + 2;
+    e->sd_cap = (unsigned)(max_frames * e->fp.Nbits);
+    e->sd_stride = (WB_CARRY_CAP + (unsigned long long)e->sd_cap + 63) & ~63ULL;
+    e->job_cap = (cfg->framing == WB_FRAMING_NONE) ? 1 : (int)((WB_CARRY_CAP + e->sd_cap) / e->dp.nsym + 2);
+    CRE(cudaMalloc(&e->d_in, e->in_stride * n));
+    CRE(cudaMalloc(&e->d_state, sizeof(wb_stream_state) * n));
+    CRE(cudaMalloc(&e->d_cursor, sizeof(wb_cursor) * n));
+    CRE(cudaMalloc(&e->d_sd, sizeof(float) * e->sd_stride * n));
+    CRE(cudaMemsetAsync(e->d_sd, 0, sizeof(float) * e->sd_stride * n, e->stream));
+    size_t nslots = (size_t)n * e->job_cap;
+    CRE(cudaMalloc(&e->d_jobs, sizeof(unsigned) * nslots));
+    CRE(cudaMalloc(&e->d_c4, sizeof(double) * nslots));
+    CRE(cudaMalloc(&e->d_cw, sizeof(wb_codeword) * nslots));
+    CRE(cudaMalloc(&e->d_cw_packed, sizeof(wb_codeword) * nslots));
+    CRE(cudaMalloc(&e->d_gather, sizeof(unsigned) * (nslots + (size_t)n + 1)));
+    CRE(cudaMalloc(&e->d_fill, sizeof(unsigned long long) * n));
+    if (cfg->flags & WB_FLAG_KEEP_LLR) {
+        CRE(cudaMalloc(&e->d_llr, sizeof(float) * WB_NCODE * nslots));
+        CRE(cudaMalloc(&e->d_llr_packed, sizeof(float) * WB_NCODE * nslots));
+    }
+    rc = upload_tables(e);
+    if (rc) { wb_destroy(e); return rc; }
+    rc = init_states(e);
+    if (rc) { wb_destroy(e); return rc; }
+    /* kernel attributes */
+    {
+        const int SPB = 32 / e->fp.M;
+        e->fsk_smem = ((sizeof(wb_fsk_sc) * SPB + 127) / 128) * 128 + (size_t)SPB * e->fp.sreg;
+        cudaError_t ce = cudaErrorInvalidValue;
+        if (e->fp.M == 2 && e->fp.Ts == 8) ce = fsk_set_attr<2, 8>(e->fsk_smem);
+        else if (e->fp.M == 2 && e->fp.Ts == 10) ce = fsk_set_attr<2, 10>(e->fsk_smem);
+        else if (e->fp.M == 4 && e->fp.Ts == 8) ce = fsk_set_attr<4, 8>(e->fsk_smem);
+        else if (e->fp.M == 4 && e->fp.Ts == 10) ce = fsk_set_attr<4, 10>(e->fsk_smem);
+        else { wb_destroy(e); return wb_fail(WB_EINVAL, "Fs/Rs = %d: only 8 and 10 samples per symbol are built", e->fp.Ts); }
+        if (ce != cudaSuccess) { wb_fail(WB_ECUDA, "fsk kernel smem %zu: %s", e->fsk_smem, cudaGetErrorString(ce)); wb_destroy(e); return WB_ECUDA; }
+        CRE(cudaFuncSetAttribute(wb_ldpc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(wb_ldpc_smem)));
+    }
+    CRE(cudaStreamSynchronize(e->stream));
+#undef CRE
+    *out = e;
+    return WB_OK;
+}
+
+/* ---- streaming path ----------------------------------------------------- */
+
+static int wb_collect(wb_engine *e);
+
+extern "C" int wb_nin(wb_engine *e, uint32_t *nin)
+{
+    if (!e || !nin) return wb_fail(WB_EINVAL, "null argument");
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    for (int s = 0; s < e->cfg.n_streams; s++) nin[s] = (uint32_t)e->nin[s];
+    return WB_OK;
+}
+
+extern "C" int wb_feed(wb_engine *e, const void *const *iq, const uint64_t *nsamp)
+{
+    if (!e || !nsamp) return wb_fail(WB_EINVAL, "null argument");
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    if (e->resident_mode) return wb_fail(WB_EINVAL, "engine is in resident (wb_dev_set_fill) mode");
+    CU(cudaSetDevice(e->cfg.device));
+    const int n = e->cfg.n_streams, bps = e->fp.in_bps;
+    for (int s = 0; s < n; s++) {
+        if (nsamp[s] == 0) continue;
+        if (!iq || !iq[s]) return wb_fail(WB_EINVAL, "stream %d: null buffer", s);
+        if (WB_HEADROOM + e->fill[s] + nsamp[s] > e->in_cap) return wb_fail(WB_ERANGE, "stream %d: chunk capacity exceeded", s);
+    }
+    /* the remainder of stream s occupies [HEADROOM - rem, HEADROOM) after a compacting wb_process, or
+       [HEADROOM, HEADROOM + fill) if nothing was processed since the last feed: fill[] counts from the
+       parked remainder's start in both cases */
+    for (int s = 0; s < n; s++) {
+        if (nsamp[s] == 0) continue;
+        unsigned long long rem = e->cursor[s].in_fill;       /* parked remainder (0 before the first process) */
+        unsigned long long off = WB_HEADROOM + (e->fill[s] - rem);
+        CU(cudaMemcpyAsync(e->d_in + (size_t)s * e->in_stride + off * bps, iq[s], nsamp[s] * bps, cudaMemcpyHostToDevice, e->stream));
+        e->fill[s] += nsamp[s];
+    }
+    for (int s = 1; s < n && e->uniform_fill; s++)
+        if (e->fill[s] - e->cursor[s].in_fill != e->fill[0] - e->cursor[0].in_fill) e->uniform_fill = false;
+    return WB_OK;
+}
+
+extern "C" int wb_feed_strided(wb_engine *e, const void *base, uint64_t stride_bytes, uint64_t nsamp)
+{
+    if (!e || !base) return wb_fail(WB_EINVAL, "null argument");
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    if (e->resident_mode) return wb_fail(WB_EINVAL, "engine is in resident (wb_dev_set_fill) mode");
+    CU(cudaSetDevice(e->cfg.device));
+    const int n = e->cfg.n_streams, bps = e->fp.in_bps;
+    if (nsamp == 0) return WB_OK;
+    /* fresh samples of every stream start at the same row offset iff (fill - parked remainder) is uniform */
+    unsigned long long fresh0 = e->fill[0] - e->cursor[0].in_fill;
+    bool uniform = true;
+    for (int s = 0; s < n; s++) {
+        if (WB_HEADROOM + e->fill[s] + nsamp > e->in_cap) return wb_fail(WB_ERANGE, "stream %d: chunk capacity exceeded", s);
+        if (e->fill[s] - e->cursor[s].in_fill != fresh0) uniform = false;
+    }
+    if (uniform) {
+        CU(cudaMemcpy2DAsync(e->d_in + (WB_HEADROOM + fresh0) * bps, e->in_stride, base, stride_bytes, nsamp * bps, n,
+                             cudaMemcpyHostToDevice, e->stream));
+        for (int s = 0; s < n; s++) e->fill[s] += nsamp;
+    } else {
+        for (int s = 0; s < n; s++) {
+            unsigned long long off = WB_HEADROOM + (e->fill[s] - e->cursor[s].in_fill);
+            CU(cudaMemcpyAsync(e->d_in + (size_t)s * e->in_stride + off * bps, (const unsigned char *)base + (size_t)s * stride_bytes,
+                               nsamp * bps, cudaMemcpyHostToDevice, e->stream));
+            e->fill[s] += nsamp;
+        }
+    }
+    return WB_OK;
+}
+
+__global__ void wb_set_fill_kernel(wb_stream_state *st, const unsigned long long *fill, int n)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    /* in_pos stays where the last process left it (headroom - parked remainder) */
+    st[s].in_fill = st[s].in_pos + fill[s];
+}
+
+__global__ void wb_gather_kernel(const wb_codeword *cw, const float *llr, const unsigned *offs, const wb_cursor *cur,
+                                 wb_codeword *cw_out, float *llr_out, int job_cap, int n_streams)
+{
+    /* one block per stream: copy its n_jobs records (and LLR rows) to the packed arrays */
+    int s = blockIdx.x;
+    unsigned nj = cur[s].n_jobs, o = offs[s];
+    const unsigned *src = reinterpret_cast<const unsigned *>(cw + (size_t)s * job_cap);
+    unsigned *dst = reinterpret_cast<unsigned *>(cw_out + o);
+    const unsigned words = nj * (unsigned)(sizeof(wb_codeword) / 4);
+    for (unsigned i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    if (llr && llr_out) {
+        const float *ls = llr + (size_t)s * job_cap * WB_NCODE;
+        float *ld = llr_out + (size_t)o * WB_NCODE;
+        for (unsigned i = threadIdx.x; i < nj * WB_NCODE; i += blockDim.x) ld[i] = ls[i];
+    }
+}
+
+template <int M, int TS>
+static void launch_fsk(wb_engine *e, const wb_fsk_args &a)
+{
+    const int SPB = 32 / M;
+    int grid = (e->cfg.n_streams + SPB - 1) / SPB;
+    wb_fsk_kernel<M, TS><<<grid, SPB * 32, e->fsk_smem, e->stream>>>(e->fp, a);
+}
+
+extern "C" int wb_process(wb_engine *e)
+{
+    if (!e) return wb_fail(WB_EINVAL, "null engine");
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    CU(cudaSetDevice(e->cfg.device));
+    const int n = e->cfg.n_streams;
+    if (!e->resident_mode) {
+        /* tell the device how many samples each stream now holds (fill counts from the parked remainder);
+           e->fill is pageable, so the copy is staged before the call returns */
+        CU(cudaMemcpyAsync(e->d_fill, e->fill.data(), sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, e->stream));
+        wb_set_fill_kernel<<<(n + 127) / 128, 128, 0, e->stream>>>(e->d_state, e->d_fill, n);
+        e->launches++;
+    }
+    wb_fsk_args a;
+    a.state = e->d_state; a.cursor = e->d_cursor; a.in = e->d_in; a.in_stride = e->in_stride;
+    a.sd = e->d_sd; a.sd_stride = e->sd_stride; a.sd_cap = e->sd_cap; a.n_streams = n;
+    a.compact = e->resident_mode ? 0 : 1; a.headroom = WB_HEADROOM;
+    a.frame_log = e->d_frame_log; a.log_cap = e->log_cap;
+    CU(cudaEventRecord(e->ev[0], e->stream));
+    if (e->fp.M == 2 && e->fp.Ts == 8) launch_fsk<2, 8>(e, a);
+    else if (e->fp.M == 2 && e->fp.Ts == 10) launch_fsk<2, 10>(e, a);
+    else if (e->fp.M == 4 && e->fp.Ts == 8) launch_fsk<4, 8>(e, a);
+    else launch_fsk<4, 10>(e, a);
+    e->launches++;
+    CU(cudaEventRecord(e->ev[1], e->stream));
+    if (e->cfg.framing != WB_FRAMING_NONE) {
+        wb_deframe_kernel<<<(n + 3) / 4, 128, 0, e->stream>>>(e->dp, e->d_state, e->d_cursor, e->d_sd, e->sd_stride,
+                                                               e->d_jobs, e->job_cap, n);
+        CU(cudaEventRecord(e->ev[2], e->stream));
+        size_t nslots = (size_t)n * e->job_cap;
+        wb_llr_stats_kernel<<<(unsigned)((nslots + 127) / 128), 128, 0, e->stream>>>(e->d_sd, e->sd_stride, e->d_jobs, e->d_c4,
+                                                                                    e->d_cursor, e->job_cap, n, e->cfg.framing, e->d_scramble);
+        CU(cudaEventRecord(e->ev[3], e->stream));
+        wb_ldpc_args la;
+        memset(&la, 0, sizeof(la));
+        la.sd = e->d_sd; la.sd_stride = e->sd_stride; la.jobs = e->d_jobs; la.c4 = e->d_c4; la.cur = e->d_cursor;
+        la.st = e->d_state; la.job_cap = e->job_cap; la.framing = e->cfg.framing; la.llr_in = nullptr;
+        la.cw = e->d_cw; la.llr_out = e->d_llr; la.max_iter = e->max_iter;
+        la.vedge = e->d_vedge; la.crc_tab = e->d_crc_tab; la.crc0 = e->crc0; la.scramble = e->d_scramble; la.lut = e->d_lut;
+        wb_ldpc_kernel<<<(unsigned)nslots, WB_LDPC_THREADS, sizeof(wb_ldpc_smem), e->stream>>>(la, 0);
+        CU(cudaEventRecord(e->ev[4], e->stream));
+        wb_carry_kernel<<<(n + 3) / 4, 128, 0, e->stream>>>(e->d_state, e->d_cursor, e->d_sd, e->sd_stride, n);
+        e->launches += 4;
+    } else {
+        CU(cudaEventRecord(e->ev[2], e->stream));
+        CU(cudaEventRecord(e->ev[3], e->stream));
+        CU(cudaEventRecord(e->ev[4], e->stream));
+    }
+    CU(cudaGetLastError());
+    e->pending = true;
+    return WB_OK;
+}
+
+/* wait for the last wb_process and bring its bookkeeping (cursors, codeword records) to the host */
+static int wb_collect(wb_engine *e)
+{
+    if (!e->pending) return WB_OK;
+    CU(cudaSetDevice(e->cfg.device));
+    const int n = e->cfg.n_streams;
+    CU(cudaMemcpyAsync(e->cursor.data(), e->d_cursor, sizeof(wb_cursor) * n, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->pending = false;
+    for (int i = 0; i < 4; i++) cudaEventElapsedTime(&e->kernel_ms[i], e->ev[i], e->ev[i + 1]);
+    uint64_t total = 0, samples = 0;
+    std::vector<unsigned> offs(n + 1);
+    for (int s = 0; s < n; s++) {
+        offs[s] = (unsigned)total;
+        if (e->cfg.framing == WB_FRAMING_NONE) e->cursor[s].n_jobs = 0;
+        total += e->cursor[s].n_jobs;
+        samples += e->cursor[s].consumed;
+        if (!e->resident_mode) e->fill[s] = e->cursor[s].in_fill;
+        e->nin[s] = e->cursor[s].nin;
+    }
+    offs[n] = (unsigned)total;
+    e->last_codewords = total;
+    e->last_samples = samples;
+    e->last_cw.resize(total);
+    e->last_llr.clear();
+    if (total) {
+        CU(cudaMemcpyAsync(e->d_gather, offs.data(), sizeof(unsigned) * (n + 1), cudaMemcpyHostToDevice, e->stream));
+        wb_gather_kernel<<<n, 256, 0, e->stream>>>(e->d_cw, e->d_llr, e->d_gather, e->d_cursor, e->d_cw_packed, e->d_llr_packed,
+                                                    e->job_cap, n);
+        e->launches++;
+        CU(cudaMemcpyAsync(e->last_cw.data(), e->d_cw_packed, sizeof(wb_codeword) * total, cudaMemcpyDeviceToHost, e->stream));
+        if (e->d_llr) {
+            e->last_llr.resize((size_t)total * WB_NCODE);
+            CU(cudaMemcpyAsync(e->last_llr.data(), e->d_llr_packed, sizeof(float) * WB_NCODE * total, cudaMemcpyDeviceToHost, e->stream));
+        }
+        CU(cudaStreamSynchronize(e->stream));
+        for (size_t i = 0; i < total; i++) {
+            const wb_codeword &c = e->last_cw[i];
+            if (c.crc_ok) e->packets[c.stream].insert(e->packets[c.stream].end(), c.bytes, c.bytes + WB_PACKET_BYTES);
+        }
+    }
+    return WB_OK;
+}
+
+extern "C" int wb_sync(wb_engine *e)
+{
+    if (!e) return wb_fail(WB_EINVAL, "null engine");
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(e->stream));
+    return WB_OK;
+}
+
+extern "C" int wb_drain_packets(wb_engine *e, int stream, uint8_t *buf, size_t cap, size_t *nbytes)
+{
+    if (!e || !nbytes) return wb_fail(WB_EINVAL, "null argument");
+    if (stream < 0 || stream >= e->cfg.n_streams) return wb_fail(WB_EINVAL, "stream %d out of range", stream);
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    std::deque<uint8_t> &q = e->packets[stream];
+    size_t n = std::min(q.size(), cap - cap % WB_PACKET_BYTES);
+    if (n && !buf) return wb_fail(WB_EINVAL, "null buffer");
+    std::copy(q.begin(), q.begin() + n, buf);
+    q.erase(q.begin(), q.begin() + n);
+    *nbytes = n;
+    return WB_OK;
+}
+
+extern "C" int wb_drain_all_packets(wb_engine *e, uint8_t *buf, size_t cap, size_t *nbytes, uint64_t *npackets)
+{
+    if (!e || !nbytes) return wb_fail(WB_EINVAL, "null argument");
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    const size_t rec = 8 + WB_PACKET_BYTES;
+    size_t need = 0;
+    for (auto &q : e->packets) need += q.size() / WB_PACKET_BYTES * rec;
+    if (need > cap) { *nbytes = need; return wb_fail(WB_ERANGE, "need %zu bytes", need); }
+    size_t o = 0; uint64_t np = 0;
+    for (int s = 0; s < e->cfg.n_streams; s++) {
+        std::deque<uint8_t> &q = e->packets[s];
+        uint32_t k = 0;
+        while (q.size() >= WB_PACKET_BYTES) {
+            int32_t ss = s;
+            memcpy(buf + o, &ss, 4); memcpy(buf + o + 4, &k, 4);
+            std::copy(q.begin(), q.begin() + WB_PACKET_BYTES, buf + o + 8);
+            q.erase(q.begin(), q.begin() + WB_PACKET_BYTES);
+            o += rec; k++; np++;
+        }
+    }
+    *nbytes = o;
+    if (npackets) *npackets = np;
+    return WB_OK;
+}
+
+extern "C" int wb_drain_soft(wb_engine *e, int stream, float *buf, size_t cap_floats, size_t *nout)
+{
+    if (!e || !nout) return wb_fail(WB_EINVAL, "null argument");
+    if (stream < 0 || stream >= e->cfg.n_streams) return wb_fail(WB_EINVAL, "stream %d out of range", stream);
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    CU(cudaSetDevice(e->cfg.device));
+    size_t n = e->cursor[stream].n_sd;
+    *nout = n;
+    if (n > cap_floats) return wb_fail(WB_ERANGE, "need %zu floats", n);
+    if (n) {
+        CU(cudaMemcpyAsync(buf, e->d_sd + (size_t)stream * e->sd_stride + WB_CARRY_CAP, sizeof(float) * n, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    return WB_OK;
+}
+
+extern "C" int wb_drain_codewords(wb_engine *e, wb_codeword *cw, float *llr, size_t cap, size_t *nout)
+{
+    if (!e || !nout) return wb_fail(WB_EINVAL, "null argument");
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    size_t n = e->last_cw.size();
+    *nout = n;
+    if (n > cap) return wb_fail(WB_ERANGE, "need %zu records", n);
+    if (n && cw) memcpy(cw, e->last_cw.data(), sizeof(wb_codeword) * n);
+    if (n && llr) {
+        if (e->last_llr.empty()) return wb_fail(WB_EINVAL, "LLRs need WB_FLAG_KEEP_LLR");
+        memcpy(llr, e->last_llr.data(), sizeof(float) * WB_NCODE * n);
+    }
+    return WB_OK;
+}
+
+extern "C" int wb_get_stats(wb_engine *e, int stream, wb_stats *out)
+{
+    if (!e || !out) return wb_fail(WB_EINVAL, "null argument");
+    if (stream < 0 || stream >= e->cfg.n_streams) return wb_fail(WB_EINVAL, "stream %d out of range", stream);
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    CU(cudaSetDevice(e->cfg.device));
+    wb_stream_state st;
+    CU(cudaMemcpyAsync(&st, e->d_state + stream, sizeof(st), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    memset(out, 0, sizeof(*out));
+    const float binw = (float)e->fp.Fs / (float)e->fp.Ndft;
+    out->ppm = st.ppm;
+    for (int m = 0; m < e->fp.M; m++) out->f_est[m] = (float)st.fbin[m] * binw;   /* reference src/fsk.c:671 */
+    out->rx_timing = st.rx_timing;
+    out->norm_rx_timing = st.norm_rx_timing;
+    out->foff = 0.0f;
+    out->nin = st.nin;
+    out->nfft = e->fp.Ndft / 2;
+    memcpy(out->samp_fft, st.fft_est, sizeof(float) * (e->fp.Ndft / 2));
+    out->frames = st.frames;
+    out->packets = st.packets;
+    out->packet_errors = st.packet_errors;
+    return WB_OK;
+}
+
+extern "C" int wb_clear_estimators(wb_engine *e)
+{
+    if (!e) return wb_fail(WB_EINVAL, "null engine");
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    /* reference src/fsk.c:505-520: zero fft_est and re-arm the first-frame f_est latch */
+    const int n = e->cfg.n_streams;
+    std::vector<wb_stream_state> h(n);
+    CU(cudaMemcpy(h.data(), e->d_state, sizeof(wb_stream_state) * n, cudaMemcpyDeviceToHost));
+    for (int s = 0; s < n; s++) {
+        memset(h[s].fft_est, 0, sizeof(h[s].fft_est));
+        for (int m = 0; m < WB_MAXM; m++) h[s].fbin[m] = 0;
+    }
+    CU(cudaMemcpy(e->d_state, h.data(), sizeof(wb_stream_state) * n, cudaMemcpyHostToDevice));
+    return WB_OK;
+}
+
+/* ---- stage-level entry points ------------------------------------------- */
+
+extern "C" int wb_ldpc_decode_batch(wb_engine *e, const float *llr, size_t n, int max_iter, uint8_t *bits_packed,
+                                    int32_t *iters, int32_t *parity_ok)
+{
+    if (!e || !llr || !bits_packed || !iters || !parity_ok) return wb_fail(WB_EINVAL, "null argument");
+    if (n == 0) return WB_OK;
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    CU(cudaSetDevice(e->cfg.device));
+    float *d_llr = nullptr; uint8_t *d_bits = nullptr; int *d_it = nullptr, *d_pc = nullptr;
+    cudaError_t ce;
+    if ((ce = cudaMalloc(&d_llr, sizeof(float) * WB_NCODE * n)) != cudaSuccess ||
+        (ce = cudaMalloc(&d_bits, 323 * n)) != cudaSuccess || (ce = cudaMalloc(&d_it, 4 * n)) != cudaSuccess ||
+        (ce = cudaMalloc(&d_pc, 4 * n)) != cudaSuccess) {
+        cudaFree(d_llr); cudaFree(d_bits); cudaFree(d_it); cudaFree(d_pc);
+        return wb_fail(WB_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(ce));
+    }
+    rc = WB_OK;
+    do {
+        if ((ce = cudaMemcpyAsync(d_llr, llr, sizeof(float) * WB_NCODE * n, cudaMemcpyHostToDevice, e->stream)) != cudaSuccess) break;
+        wb_ldpc_args la;
+        memset(&la, 0, sizeof(la));
+        la.llr_in = d_llr; la.bits_out = d_bits; la.iters_out = d_it; la.pcc_out = d_pc;
+        la.max_iter = max_iter > 0 ? max_iter : e->max_iter;
+        la.vedge = e->d_vedge; la.crc_tab = e->d_crc_tab; la.crc0 = e->crc0; la.scramble = e->d_scramble; la.lut = e->d_lut;
+        wb_ldpc_kernel<<<(unsigned)n, WB_LDPC_THREADS, sizeof(wb_ldpc_smem), e->stream>>>(la, (long long)n);
+        e->launches++;
+        if ((ce = cudaGetLastError()) != cudaSuccess) break;
+        if ((ce = cudaMemcpyAsync(bits_packed, d_bits, 323 * n, cudaMemcpyDeviceToHost, e->stream)) != cudaSuccess) break;
+        if ((ce = cudaMemcpyAsync(iters, d_it, 4 * n, cudaMemcpyDeviceToHost, e->stream)) != cudaSuccess) break;
+        if ((ce = cudaMemcpyAsync(parity_ok, d_pc, 4 * n, cudaMemcpyDeviceToHost, e->stream)) != cudaSuccess) break;
+        ce = cudaStreamSynchronize(e->stream);
+    } while (0);
+    cudaFree(d_llr); cudaFree(d_bits); cudaFree(d_it); cudaFree(d_pc);
+    if (ce != cudaSuccess) return wb_fail(WB_ECUDA, "wb_ldpc_decode_batch: %s", cudaGetErrorString(ce));
+    return rc;
+}
+
+extern "C" int wb_sd_to_llr_batch(wb_engine *e, const float *sd, size_t n, float *llr)
+{
+    if (!e || !sd || !llr) return wb_fail(WB_EINVAL, "null argument");
+    if (n == 0) return WB_OK;
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    CU(cudaSetDevice(e->cfg.device));
+    float *d_sd = nullptr, *d_llr = nullptr; double *d_c4 = nullptr;
+    cudaError_t ce;
+    if ((ce = cudaMalloc(&d_sd, sizeof(float) * WB_NCODE * n)) != cudaSuccess ||
+        (ce = cudaMalloc(&d_llr, sizeof(float) * WB_NCODE * n)) != cudaSuccess ||
+        (ce = cudaMalloc(&d_c4, sizeof(double) * n)) != cudaSuccess) {
+        cudaFree(d_sd); cudaFree(d_llr); cudaFree(d_c4);
+        return wb_fail(WB_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(ce));
+    }
+    do {
+        if ((ce = cudaMemcpyAsync(d_sd, sd, sizeof(float) * WB_NCODE * n, cudaMemcpyHostToDevice, e->stream)) != cudaSuccess) break;
+        wb_llr_stats_plain_kernel<<<(unsigned)((n + 127) / 128), 128, 0, e->stream>>>(d_sd, d_c4, (long long)n);
+        wb_llr_scale_kernel<<<(unsigned)((n * WB_NCODE + 255) / 256), 256, 0, e->stream>>>(d_sd, d_c4, d_llr, (long long)n);
+        e->launches += 2;
+        if ((ce = cudaGetLastError()) != cudaSuccess) break;
+        if ((ce = cudaMemcpyAsync(llr, d_llr, sizeof(float) * WB_NCODE * n, cudaMemcpyDeviceToHost, e->stream)) != cudaSuccess) break;
+        ce = cudaStreamSynchronize(e->stream);
+    } while (0);
+    cudaFree(d_sd); cudaFree(d_llr); cudaFree(d_c4);
+    if (ce != cudaSuccess) return wb_fail(WB_ECUDA, "wb_sd_to_llr_batch: %s", cudaGetErrorString(ce));
+    return WB_OK;
+}
+
+/* ---- HBM-resident benchmarking helpers ---------------------------------- */
+
+extern "C" int wb_dev_input(wb_engine *e, void **dptr, uint64_t *stride_bytes, uint64_t *capacity_samples)
+{
+    if (!e) return wb_fail(WB_EINVAL, "null engine");
+    if (dptr) *dptr = e->d_in + (size_t)WB_HEADROOM * e->fp.in_bps;
+    if (stride_bytes) *stride_bytes = e->in_stride;
+    if (capacity_samples) *capacity_samples = e->cfg.chunk_samples;
+    return WB_OK;
+}
+
+__global__ void wb_rewind_kernel(wb_stream_state *st, int n, unsigned headroom, unsigned long long nsamp)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    st[s].in_pos = headroom;
+    st[s].in_fill = headroom + nsamp;
+}
+
+extern "C" int wb_dev_set_fill(wb_engine *e, uint64_t nsamp)
+{
+    if (!e) return wb_fail(WB_EINVAL, "null engine");
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    if (nsamp > e->cfg.chunk_samples) return wb_fail(WB_ERANGE, "nsamp exceeds chunk_samples");
+    CU(cudaSetDevice(e->cfg.device));
+    e->resident_mode = true;
+    wb_rewind_kernel<<<(e->cfg.n_streams + 127) / 128, 128, 0, e->stream>>>(e->d_state, e->cfg.n_streams, WB_HEADROOM, nsamp);
+    e->launches++;
+    CU(cudaGetLastError());
+    return WB_OK;
+}
+
+__global__ void wb_replicate_kernel(unsigned char *in, unsigned long long stride, int n_src, int n_streams,
+                                    unsigned long long nbytes, unsigned long long rot_bytes, unsigned headroom_bytes)
+{
+    /* stream s >= n_src := source (s % n_src) rotated left by (s / n_src) * rot bytes; 16-byte granules */
+    int s = n_src + blockIdx.y;
+    if (s >= n_streams) return;
+    const unsigned char *src = in + (size_t)(s % n_src) * stride + headroom_bytes;
+    unsigned char *dst = in + (size_t)s * stride + headroom_bytes;
+    unsigned long long r = ((unsigned long long)(s / n_src) * rot_bytes) % nbytes;
+    unsigned long long ng = nbytes / 16;
+    for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long so = (g * 16 + r) % nbytes;
+        uint4 v;
+        if (so + 16 <= nbytes && (so & 15) == 0) v = *reinterpret_cast<const uint4 *>(src + so);
+        else {
+            unsigned char t[16];
+            for (int b = 0; b < 16; b++) t[b] = src[(so + b) % nbytes];
+            memcpy(&v, t, 16);
+        }
+        *reinterpret_cast<uint4 *>(dst + g * 16) = v;
+    }
+}
+
+extern "C" int wb_dev_replicate(wb_engine *e, int n_src, uint64_t nsamp, uint64_t rot)
+{
+    if (!e) return wb_fail(WB_EINVAL, "null engine");
+    if (n_src <= 0 || n_src > e->cfg.n_streams) return wb_fail(WB_EINVAL, "n_src out of range");
+    if (nsamp > e->cfg.chunk_samples) return wb_fail(WB_ERANGE, "nsamp exceeds chunk_samples");
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    CU(cudaSetDevice(e->cfg.device));
+    const int bps = e->fp.in_bps;
+    unsigned long long nbytes = nsamp * bps;
+    if (nbytes % 16) return wb_fail(WB_EINVAL, "nsamp * bytes-per-sample must be a multiple of 16");
+    if ((rot * bps) % 16) return wb_fail(WB_EINVAL, "rot * bytes-per-sample must be a multiple of 16");
+    int rest = e->cfg.n_streams - n_src;
+    if (rest > 0) {
+        dim3 grid(64, rest);
+        wb_replicate_kernel<<<grid, 256, 0, e->stream>>>(e->d_in, e->in_stride, n_src, e->cfg.n_streams, nbytes, rot * bps,
+                                                        WB_HEADROOM * bps);
+        e->launches++;
+        CU(cudaGetLastError());
+    }
+    return WB_OK;
+}
+
+__global__ void wb_replicate_llr_kernel(float *llr, size_t n_src, size_t n)
+{
+    size_t total = n * WB_NCODE;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x + n_src * WB_NCODE; i < total; i += (size_t)gridDim.x * blockDim.x)
+        llr[i] = llr[i % (n_src * WB_NCODE)];
+}
+
+extern "C" int wb_dev_ldpc_setup(wb_engine *e, const float *llr, size_t n_src, size_t n)
+{
+    if (!e || !llr || n_src == 0 || n < n_src) return wb_fail(WB_EINVAL, "bad argument");
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    CU(cudaSetDevice(e->cfg.device));
+    cudaFree(e->d_bench_llr); cudaFree(e->d_bench_bits); cudaFree(e->d_bench_iters); cudaFree(e->d_bench_pcc);
+    e->d_bench_llr = nullptr; e->d_bench_bits = nullptr; e->d_bench_iters = e->d_bench_pcc = nullptr; e->bench_n = 0;
+    if (cudaMalloc(&e->d_bench_llr, sizeof(float) * WB_NCODE * n) != cudaSuccess || cudaMalloc(&e->d_bench_bits, 323 * n) != cudaSuccess ||
+        cudaMalloc(&e->d_bench_iters, 4 * n) != cudaSuccess || cudaMalloc(&e->d_bench_pcc, 4 * n) != cudaSuccess)
+        return wb_fail(WB_ENOMEM, "cudaMalloc LDPC bench buffers");
+    CU(cudaMemcpyAsync(e->d_bench_llr, llr, sizeof(float) * WB_NCODE * n_src, cudaMemcpyHostToDevice, e->stream));
+    if (n > n_src) {
+        wb_replicate_llr_kernel<<<1184, 256, 0, e->stream>>>(e->d_bench_llr, n_src, n);
+        e->launches++;
+    }
+    CU(cudaStreamSynchronize(e->stream));
+    e->bench_n = n;
+    return WB_OK;
+}
+
+extern "C" int wb_dev_ldpc_run(wb_engine *e, int max_iter)
+{
+    if (!e || !e->bench_n) return wb_fail(WB_EINVAL, "wb_dev_ldpc_setup first");
+    CU(cudaSetDevice(e->cfg.device));
+    wb_ldpc_args la;
+    memset(&la, 0, sizeof(la));
+    la.llr_in = e->d_bench_llr; la.bits_out = e->d_bench_bits; la.iters_out = e->d_bench_iters; la.pcc_out = e->d_bench_pcc;
+    la.max_iter = max_iter > 0 ? max_iter : e->max_iter;
+    la.vedge = e->d_vedge; la.crc_tab = e->d_crc_tab; la.crc0 = e->crc0; la.scramble = e->d_scramble; la.lut = e->d_lut;
+    wb_ldpc_kernel<<<(unsigned)e->bench_n, WB_LDPC_THREADS, sizeof(wb_ldpc_smem), e->stream>>>(la, (long long)e->bench_n);
+    e->launches++;
+    CU(cudaGetLastError());
+    return WB_OK;
+}
+
+extern "C" int wb_dev_ldpc_result(wb_engine *e, size_t first, size_t n, uint8_t *bits_packed, int32_t *iters, int32_t *parity_ok)
+{
+    if (!e || first + n > e->bench_n) return wb_fail(WB_EINVAL, "range");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    if (bits_packed) CU(cudaMemcpy(bits_packed, e->d_bench_bits + first * 323, 323 * n, cudaMemcpyDeviceToHost));
+    if (iters) CU(cudaMemcpy(iters, e->d_bench_iters + first, 4 * n, cudaMemcpyDeviceToHost));
+    if (parity_ok) CU(cudaMemcpy(parity_ok, e->d_bench_pcc + first, 4 * n, cudaMemcpyDeviceToHost));
+    return WB_OK;
+}
+
+extern "C" int wb_timer_start(wb_engine *e)
+{
+    if (!e) return wb_fail(WB_EINVAL, "null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaEventRecord(e->tev0, e->stream));
+    return WB_OK;
+}
+
+extern "C" int wb_timer_stop(wb_engine *e, float *ms)
+{
+    if (!e || !ms) return wb_fail(WB_EINVAL, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaEventRecord(e->tev1, e->stream));
+    CU(cudaEventSynchronize(e->tev1));
+    CU(cudaEventElapsedTime(ms, e->tev0, e->tev1));
+    return WB_OK;
+}
+
+extern "C" int wb_last_kernel_ms(wb_engine *e, float *ms)
+{
+    if (!e || !ms) return wb_fail(WB_EINVAL, "null argument");
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    for (int i = 0; i < 4; i++) ms[i] = e->kernel_ms[i];
+    return WB_OK;
+}
+
+extern "C" uint64_t wb_launch_count(wb_engine *e) { return e ? e->launches : 0; }
+extern "C" uint64_t wb_last_codewords(wb_engine *e) { if (!e || wb_collect(e)) return 0; return e->last_codewords; }
+extern "C" uint64_t wb_last_samples(wb_engine *e) { if (!e || wb_collect(e)) return 0; return e->last_samples; }
+
+/* test tap: per-frame log of the next wb_process calls (8 floats per frame: nin, bins[4], norm_rx_timing, ppm, rx_timing) */
+extern "C" int wb_enable_frame_log(wb_engine *e, int frames_per_stream)
+{
+    if (!e || frames_per_stream < 0) return wb_fail(WB_EINVAL, "bad argument");
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    CU(cudaSetDevice(e->cfg.device));
+    cudaFree(e->d_frame_log); e->d_frame_log = nullptr; e->log_cap = 0;
+    if (frames_per_stream) {
+        size_t bytes = sizeof(float) * 8 * (size_t)frames_per_stream * e->cfg.n_streams;
+        if (cudaMalloc(&e->d_frame_log, bytes) != cudaSuccess) return wb_fail(WB_ENOMEM, "cudaMalloc frame log");
+        CU(cudaMemset(e->d_frame_log, 0, bytes));
+        e->log_cap = frames_per_stream;
+    }
+    return WB_OK;
+}
+
+extern "C" int wb_read_frame_log(wb_engine *e, int stream, float *buf, size_t cap_frames)
+{
+    if (!e || !buf || !e->d_frame_log) return wb_fail(WB_EINVAL, "frame log not enabled");
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    CU(cudaSetDevice(e->cfg.device));
+    size_t nfr = std::min((size_t)e->log_cap, cap_frames);
+    CU(cudaMemcpy(buf, e->d_frame_log + (size_t)stream * e->log_cap * 8, sizeof(float) * 8 * nfr, cudaMemcpyDeviceToHost));
+    return WB_OK;
+}
+
+/* pinned host memory for the caller's staging buffers (the e2e path copies from these) */
+extern "C" void *wb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { wb_fail(WB_ENOMEM, "cudaHostAlloc %zu", bytes); return nullptr; }
+    return p;
+}
+extern "C" void wb_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+/* geometry the host wrapper needs */
+extern "C" int wb_geometry(wb_engine *e, int32_t *out, int n)
+{
+    if (!e || !out) return wb_fail(WB_EINVAL, "null argument");
+    int32_t g[12] = {e->fp.N, e->fp.Nbits, e->fp.Ts, e->fp.P, e->fp.Ndft, e->fp.nmax, e->job_cap, (int32_t)e->sd_cap,
+                     e->fp.Nsym, e->fp.M, e->max_iter, e->dp.nsym};
+    for (int i = 0; i < n && i < 12; i++) out[i] = g[i];
+    return WB_OK;
+}

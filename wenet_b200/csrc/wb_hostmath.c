@@ -46,3 +46,11 @@ void wbh_phi0(const float *x, float *out, long n)
     wb_phi0_build(&lut);
     for (i = 0; i < n; i++) out[i] = wb_phi0_eval(&lut, x[i]);
 }
+
+void wbh_phi0_compact(const float *x, float *out, long n)
+{
+    long i;
+    static wb_phi0_compact c;
+    wb_phi0_build_compact(&c);
+    for (i = 0; i < n; i++) out[i] = wb_phi0_eval_compact(&c, x[i]);
+}

@@ -1,0 +1,96 @@
+/*
+ * wb_internal.h -- device-visible parameter blocks and per-stream state.
+ *
+ * HBM layout (one engine = one GPU):
+ *   d_in      [n_streams][in_stride]  raw input samples in cfg.in_fmt (cf32: 8 B, cs16: 4 B, cu8/s16: 2 B)
+ *   d_state   [n_streams]             wb_stream_state (persistent modem + deframer state)
+ *   d_sd      [n_streams][sd_stride]  float soft decisions: [carry of a half-collected packet | this chunk]
+ *                                     the chunk starts at float index WB_CARRY_CAP of the row
+ *   d_cursor  [n_streams]             wb_cursor (what the host reads back after every wb_process)
+ *   d_jobs    [n_streams][job_cap]    unsigned: row offset of the first collected symbol of each codeword
+ *   d_c4      [n_streams][job_cap]    double: 4 * estEsN0 of each codeword (sd_to_llr statistics)
+ *   d_cw      [n_streams][job_cap]    wb_codeword records (LDPC + CRC output)
+ *   d_llr     [n_streams][job_cap][2580] float LLRs, only with WB_FLAG_KEEP_LLR
+ */
+#ifndef WB_INTERNAL_H
+#define WB_INTERNAL_H
+
+#include <stdint.h>
+#include "wenet_b200.h"
+#include "wb_tables.h"
+
+#define WB_MAXM 4
+#define WB_MAX_NDFT 256                /* estimator FFT size the kernels are laid out for */
+#define WB_MAX_TS 10                   /* samples per symbol (v1: 8, v2: 10) */
+#define WB_MAX_NSTASH (4 * WB_MAX_TS)
+#define WB_MAX_NIN 512                 /* N + Ts/2 must not exceed this */
+#define WB_MAX_LEVELS 8
+#define WB_FRAME_SYMS 48               /* nsyms, reference src/fsk.c:134 */
+#define WB_FSK_THREADS 512             /* 16 stream-warps (2-FSK) / 8 stream-warps x 2 CTAs' worth (4-FSK: 256) */
+
+#define WB_PKT_BODY_BYTES 323          /* 256 payload + 2 crc + 65 parity */
+#define WB_CARRY_CAP 3264              /* >= 3230 symbols of a half-collected v1 packet, 64-float aligned */
+
+#define WB_LDPC_THREADS 288            /* 9 warps: 516 checks = 2 rounds, 2580 variables = 9 rounds */
+#define WB_LDPC_SLOTS 14               /* edge slots per check: 12 H1 + parity j-1 + parity j */
+#define WB_LDPC_NMSG (WB_LDPC_SLOTS * WB_NPAR)   /* 7224 message words (slot 12 of check 0 is unused) */
+
+struct wb_fsk_params {
+    int Fs, Rs, Ts, P, M, N, Nsym, Nmem, Nbits, Ndft, nstash;
+    int step;                 /* Ts / P */
+    int nint;                 /* (Nsym + 1) * P integrator outputs per frame */
+    int nsteps;               /* Nmem - step mixer steps per frame */
+    int nmax;                 /* N + Ts/2: longest frame */
+    int f_min, f_max, f_zero; /* estimator bin limits, reference src/fsk.c:568-570 */
+    float tc;                 /* 0.95 * Ndft / Fs, reference src/fsk.c:573 */
+    int n_levels;             /* FFT schedule, leaf first */
+    int lev_p[WB_MAX_LEVELS], lev_m[WB_MAX_LEVELS], lev_fstride[WB_MAX_LEVELS];
+    int in_fmt, in_bps;       /* bytes per input sample */
+    int xlen, blen, sreg;     /* smem geometry: float2 per stream for x / the other tones, bytes per stream */
+    /* host-built constant tables (glibc cosf/sinf on the host = what the reference would use) */
+    const float  *hann;       /* [Ndft]       reference src/fsk.c:94-111 */
+    const float2 *tw;         /* [Ndft]       kiss_fft twiddles, reference src/kiss_fft.c:357-363 */
+    const uint16_t *perm;     /* [Ndft]       leaf load order of the DIT recursion */
+    const float2 *pft;        /* [nint]       fine-timing oscillator, reference src/fsk.c:858-873 */
+    const float2 *dphi;       /* [Ndft/2]     comp_exp_j(2 pi f/Fs), f = bin*Fs/Ndft, src/fsk.c:763 */
+    const float2 *back;       /* [3][Ndft/2]  phase back-off for nin = N-Ts/2, N, N+Ts/2, src/fsk.c:758 */
+};
+
+struct wb_stream_state {
+    /* demodulator, reference struct FSK src/fsk.h:43-90 */
+    float2 phi_c[WB_MAXM];
+    int    fbin[WB_MAXM];     /* f_est as estimator bins (f_est = bin * Fs/Ndft) */
+    float  norm_rx_timing, ppm;
+    int    nin;
+    float  rx_timing;
+    unsigned long long frames;
+    float  fft_est[WB_MAX_NDFT / 2];
+    float2 samp_old[WB_MAX_NSTASH];
+    /* deframer, reference locals of main() src/drs232_ldpc.c:106-118 */
+    unsigned long long window;  /* bit_buffer, newest bit = bit 0 */
+    int    collecting, ind;
+    unsigned int seq;           /* codewords found so far (= packets) */
+    unsigned int packets, packet_errors;
+    unsigned int pad0;
+    /* buffer cursors */
+    unsigned long long in_pos, in_fill;   /* samples */
+};
+
+/* read back by the host after each wb_process */
+struct wb_cursor {
+    unsigned long long in_fill;   /* samples left resident (after compaction) */
+    unsigned long long consumed;  /* samples demodulated by this wb_process */
+    unsigned int n_sd;            /* soft decisions produced by this wb_process */
+    unsigned int n_jobs;          /* codewords found by this wb_process */
+    unsigned int seq0;            /* sequence number of the first of them */
+    int nin;                      /* fsk_nin() for the next frame */
+};
+
+struct wb_deframe_params {
+    int mode;                 /* WB_FRAMING_V1 / V2 */
+    int uw_bits, uw_thresh;
+    int nsym;                 /* symbols collected per packet: 3230 (v1) / 2584 (v2) */
+    unsigned long long uw, uw_mask;
+};
+
+#endif

@@ -88,4 +88,50 @@ WB_HD float wb_phi0_eval(const wb_phi0_lut *lut, float x)
     return (x < en.thr) ? en.vlo : en.vhi;
 }
 
+
+/* ---- compact form for shared memory (2.8 KB instead of 18 KB) ------------
+ * sidx[b] = step the bucket STARTS in; step[s] = {first argument of step s+1, value of step s,
+ * value of step s+1}.  A bucket holds at most one breakpoint, so either the bucket's arguments all
+ * lie below step[s].thr (-> vlo) or the compare splits them exactly where the reference does. */
+#define WB_PHI0_NSTEP_ENTRIES (WB_PHI0_NSTEPS + 1)
+typedef struct {
+    wb_phi0_entry step[WB_PHI0_NSTEP_ENTRIES];       /* 104 x 16 B */
+    uint8_t sidx[(WB_PHI0_NENTRY + 15) / 16 * 16];   /* 1153 -> 1168 B */
+} wb_phi0_compact;
+
+static inline int wb_phi0_build_compact(wb_phi0_compact *c)
+{
+    int b, k, s;
+    wb_phi0_lut full;
+    if (wb_phi0_build(&full) != 0) return -1;
+    for (s = 0; s < WB_PHI0_NSTEPS; s++) {
+        c->step[s].vlo = wb_phi0_val[s];
+        if (s + 1 < WB_PHI0_NSTEPS) {
+            c->step[s].thr = (float)((double)wb_phi0_brk[s + 1] / 65536.0);
+            c->step[s].vhi = wb_phi0_val[s + 1];
+        } else {
+            c->step[s].thr = 32768.0f;               /* cvttss2si overflow: x >= 32768 -> 10.0 */
+            c->step[s].vhi = 10.0f;
+        }
+        c->step[s].pad = 0.0f;
+    }
+    c->step[WB_PHI0_NSTEPS] = c->step[WB_PHI0_NSTEPS - 1];
+    for (b = 0; b < (int)sizeof(c->sidx); b++) c->sidx[b] = 0;
+    for (b = 0; b < WB_PHI0_NBUCKET; b++) {
+        int E = -14 + b / 64, j = b % 64;
+        int64_t q_first = (((int64_t)(64 + j)) << (E + 30)) >> 20;
+        s = 0;
+        for (k = 0; k < WB_PHI0_NSTEPS; k++) if ((int64_t)wb_phi0_brk[k] <= q_first) s = k;
+        c->sidx[b] = (uint8_t)s;
+    }
+    c->sidx[WB_PHI0_NBUCKET] = (uint8_t)(WB_PHI0_NSTEPS - 1);
+    return 0;
+}
+
+WB_HD float wb_phi0_eval_compact(const wb_phi0_compact *c, float x)
+{
+    wb_phi0_entry en = c->step[c->sidx[wb_phi0_bucket(x)]];
+    return (x < en.thr) ? en.vlo : en.vhi;
+}
+
 #endif /* WB_PHI0_H */
