@@ -1,0 +1,411 @@
+#!/usr/bin/env python3
+"""bench.py -- IQ Msamples/s demodulated AND decoded (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W                  # this engine
+    python bench.py --impl reference --gpus N --steps K --warmup W # the reference CPU pipe on the host cores
+
+Workload (config.workload): BASELINE.json configs[3], "end-to-end demod+deframe+LDPC: 4096 streams, Eb/N0
+sweep 4-12 dB", time-chunked: one STEP = one pass of the whole path (K1 fsk -> K2 deframe -> K3 llr stats
+-> K4 ldpc+crc) over one HBM-resident chunk of `--chunk` samples of every one of the 4096 streams of this
+GPU (v1 RS232 framing, 921416 sps / 115177 baud 2-FSK, cf32).  configs[3] as written (8 Msample per stream)
+is 256 GB of cf32 and does not fit one GPU, so it runs as consecutive chunks with the per-stream state carried
+in HBM; every step demodulates a full chunk.  Multi-GPU: weak scaling, 4096 streams per GPU, no collective.
+
+`value`  : whole-job Msamples/s with the chunk already resident in HBM (CUDA events on the engine's stream).
+`e2e`    : the same metric through the public API with HOST buffers: wb_feed_strided (pinned host -> HBM),
+           wb_process, wb_sync, wb_drain_all_packets (HBM -> host) every step, wall clock around device syncs.
+`roofline`: the dominant kernel (wb_fsk_kernel): algorithmic bytes (8.5 B per IQ sample) / its
+           event-timed duration, against the measured HBM peak in MEASURED_PEAKS.json.
+`cpu_baseline`: the reference's own binaries (oracle/_ref: fsk_demod | drs232_ldpc, built from the unmodified
+           sources) on the host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+EBNO_SWEEP = [4.0, 6.0, 8.0, 10.0, 12.0]
+ALG_BYTES_PER_SAMPLE_FSK = 8.5          # cf32 in (8 B) + 48 floats out per 384 samples (0.5 B), SURVEY 8(d)
+METRIC = "IQ Msamples/s demodulated+decoded"
+UNIT = "Msamples/s"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ---------------------------------------------------------------- synthetic input
+
+def make_sources(n_src, nsamp, seed_base):
+    """n_src distinct v1 streams (seeded), Eb/N0 cycling through the 4-12 dB sweep."""
+    from wenet_b200 import siggen
+    out = []
+    for i in range(n_src):
+        raw, _ = siggen.make_stream(seed_base + i, n_samples=nsamp, ebno_db=EBNO_SWEEP[i % len(EBNO_SWEEP)],
+                                    fmt="cf32", clock_ppm=float((i % 7 - 3) * 400))
+        out.append(raw)
+    return out
+
+
+# ---------------------------------------------------------------- clocks
+
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows = []
+        self.proc = None
+        exe = shutil.which("nvidia-smi")
+        if not exe:
+            return
+        try:
+            self.proc = subprocess.Popen([exe, "-i", str(device), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 9]
+        if not rows:
+            rows = [r for (t, r) in self.rows if len(r) >= 9][-5:]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[1]) for r in rows if r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(rows)}
+
+
+# ---------------------------------------------------------------- the reference CPU pipe
+
+def ref_binaries():
+    d = os.path.join(ROOT, "oracle", "_ref")
+    f, g = os.path.join(d, "fsk_demod"), os.path.join(d, "drs232_ldpc")
+    return (f, g) if os.path.exists(f) and os.path.exists(g) else None
+
+
+def run_cpu_pipes(path, n_pipes):
+    """n_pipes x (fsk_demod --cs16 -s 2 921416 115177 file - | drs232_ldpc - -), all at once. -> (wall s, bytes out)"""
+    f, g = ref_binaries()
+    cmd = "%s --cs16 -s 2 921416 115177 %s - 2>/dev/null | %s - - 2>/dev/null | wc -c" % (f, path, g)
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen(["bash", "-c", cmd], stdout=subprocess.PIPE, text=True) for _ in range(n_pipes)]
+    outs = [p.communicate()[0] for p in procs]
+    dt = time.perf_counter() - t0
+    return dt, sum(int(o.strip() or 0) for o in outs)
+
+
+def run_cpu_port(raw_cs16, n_threads):
+    """fallback when oracle/_ref is absent: the C restatement (oracle/liboracle.so), one stream per thread"""
+    from oracle import oracle as O
+    port = O.Oracle("port")
+    nbytes = [0] * n_threads
+
+    def work(i):
+        sd, _, _ = port.fsk(921416, 115177, M=2).run(raw_cs16, "cs16")
+        nbytes[i] = len(port.deframer("v1", 10).feed(sd)["packets"])
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work, args=(i,)) for i in range(n_threads)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    return time.perf_counter() - t0, sum(nbytes)
+
+
+def cpu_sample_file(nsamp, tmpdir):
+    """cs16 file: a 10 dB v1 stream (the Eb/N0 of BASELINE.json configs[0]) tiled to nsamp samples"""
+    from wenet_b200 import siggen
+    base, _ = siggen.make_stream(0, n_samples=1 << 20, ebno_db=10.0, fmt="cs16")
+    reps = max(1, nsamp // (1 << 20))
+    path = os.path.join(tmpdir, "wb_cpu_sample.cs16")
+    with open(path, "wb") as fh:
+        for _ in range(reps):
+            fh.write(base.tobytes())
+    return path, reps * (1 << 20), base
+
+
+def cpu_baseline(nsamp_per_pipe, reps=1):
+    cores = os.cpu_count() or 1
+    tmpdir = tempfile.mkdtemp(prefix="wb_bench_")
+    try:
+        path, ns, base = cpu_sample_file(nsamp_per_pipe, tmpdir)
+        if ref_binaries():
+            kind, pipes = "reference", max(1, cores // 2)
+            best = None
+            for _ in range(reps):
+                dt, nb = run_cpu_pipes(path, pipes)
+                best = dt if best is None else min(best, dt)
+            used = min(cores, 2 * pipes)
+        else:
+            kind, pipes = "port", max(1, cores)
+            raw = np.tile(base, ns // (1 << 20))
+            best, nb = run_cpu_port(raw, pipes)
+            used = pipes
+        return {"value": round(pipes * ns / best / 1e6, 3), "unit": UNIT, "cores": used, "kind": kind,
+                "sample": "%d parallel pipes (fsk_demod --cs16 -s 2 921416 115177 | drs232_ldpc) x %d samples of a 10 dB "
+                          "v1 stream each, %.2f s wall, %d B decoded" % (pipes, ns, best, nb)}
+    finally:
+        shutil.rmtree(tmpdir, ignore_errors=True)
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the reference's own CPU implementation on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    tmpdir = tempfile.mkdtemp(prefix="wb_bench_")
+    try:
+        path, ns, base = cpu_sample_file(args.cpu_samples, tmpdir)
+        have = ref_binaries() is not None
+        pipes = max(1, cores // 2) if have else max(1, cores)
+        raw = None if have else np.tile(base, ns // (1 << 20))
+        times, nb = [], 0
+        for i in range(args.warmup + args.steps):
+            dt, nb = run_cpu_pipes(path, pipes) if have else run_cpu_port(raw, pipes)
+            if i >= args.warmup:
+                times.append(dt)
+        total = sum(times)
+        value = pipes * ns * len(times) / total / 1e6
+        line = {
+            "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / len(times), 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": min(cores, 2 * pipes) if have else pipes,
+                             "kind": "reference" if have else "port",
+                             "sample": "each step: %d parallel pipes x %d samples (10 dB v1 stream, cs16), %d B decoded per step"
+                                       % (pipes, ns, nb)},
+            "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
+    finally:
+        shutil.rmtree(tmpdir, ignore_errors=True)
+
+
+# ---------------------------------------------------------------- this engine
+
+def workload_config(args, world):
+    return {"workload": "BASELINE.json configs[3] time-chunked: end-to-end 2-FSK demod + v1 deframe + LDPC(2580,2064) "
+                        "max_iter 10 + CRC, %d streams/GPU x %d-sample chunks, Eb/N0 sweep 4-12 dB, Fs 921416 Rs 115177"
+                        % (args.streams, args.chunk),
+            "streams_per_gpu": args.streams, "chunk_samples": args.chunk, "in_fmt": "cf32", "framing": "v1",
+            "ldpc_max_iter": 10, "parallelism": "stream-sharded x%d, no collective" % world,
+            "l2": "inputs (%.1f GB per step per GPU) larger than L2" % (args.streams * args.chunk * 8 / 1e9),
+            "e2e_chunk_samples": args.e2e_chunk}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=4096, help="streams per GPU")
+    ap.add_argument("--chunk", type=int, default=1 << 20, help="samples per stream per step (HBM-resident)")
+    ap.add_argument("--e2e-chunk", type=int, default=1 << 17, help="samples per stream per e2e step (pinned host)")
+    ap.add_argument("--sources", type=int, default=40, help="distinct synthetic streams generated on the host")
+    ap.add_argument("--cpu-samples", type=int, default=32 << 20, help="samples per CPU pipe (reference arm)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return 0
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    from wenet_b200 import engine as E          # raises if libwenet_b200.so is missing: no CPU fallback
+
+    n, chunk = args.streams, args.chunk
+    n_src = min(args.sources, n)
+    sources = make_sources(n_src, chunk, seed_base=rank * 1000)
+
+    eng = E.Engine(n, in_fmt="cf32", framing="v1", chunk_samples=chunk, device=local)
+    eng.feed(sources + [None] * (n - n_src))
+    eng.sync()
+    eng.dev_replicate(n_src, chunk, 4096 + 16 * 37)     # stream s = source s % n_src rotated by (s // n_src) * 4688 samples
+    eng.dev_set_fill(chunk)
+
+    def one_step():
+        eng.dev_set_fill(chunk)
+        eng.process()
+
+    attempts = 0
+    while True:
+        attempts += 1
+        clocks = ClockSampler(local)
+        for _ in range(args.warmup):
+            one_step()
+        eng.sync()
+        kms = np.zeros(4)
+        barrier()
+        l0 = eng.launch_count
+        t0 = time.perf_counter()
+        eng.timer_start()
+        for _ in range(args.steps):
+            one_step()
+        ms = eng.timer_stop()
+        t1 = time.perf_counter()
+        l1 = eng.launch_count
+        barrier()
+        clk = clocks.summary(t0, t1)
+        clocks.stop()
+        bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(clk.get("reasons", []))
+        if not bad or attempts >= 2:
+            break
+    # per-kernel split and work done, from the last timed step (every step does the same work)
+    kms = eng.last_kernel_ms().astype(np.float64)
+    samples_step = eng.last_samples
+    codewords_step = eng.last_codewords
+    pk = eng.drain_all_packets()
+    packets_last = int(len(pk))
+    ms = max_over_ranks(ms)
+    total_samples = sum_over_ranks(float(samples_step)) * args.steps
+    value = total_samples / (ms * 1e-3) / 1e6
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    fsk_gbs = ALG_BYTES_PER_SAMPLE_FSK * samples_step / (kms[0] * 1e-3) / 1e9 if kms[0] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "wb_fsk_kernel", "achieved": round(fsk_gbs, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(fsk_gbs / peak, 4), "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "kernel_ms": {"fsk": round(float(kms[0]), 3), "deframe": round(float(kms[1]), 3),
+                              "llr_stats": round(float(kms[2]), 3), "ldpc": round(float(kms[3]), 3)},
+                "alg_bytes_per_launch": ALG_BYTES_PER_SAMPLE_FSK * samples_step}
+
+    # ---- e2e through the public API with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        ec = args.e2e_chunk
+        eng.close()
+        eng2 = E.Engine(n, in_fmt="cf32", framing="v1", chunk_samples=ec + 1024, device=local)
+        pin = E.PinnedBuffer((n, 2 * ec), np.float32)
+        for s in range(n):
+            src = sources[s % n_src]
+            r = ((s // n_src) * 4688) % (chunk - ec) if chunk > ec else 0
+            pin.array[s, :] = src[2 * r:2 * r + 2 * ec]
+        d2h = 0
+
+        def e2e_step():
+            nonlocal d2h
+            eng2.feed_strided(pin.array)
+            eng2.process()
+            eng2.sync()
+            out = eng2.drain_all_packets()
+            d2h = out.nbytes + n * 40 + eng2.last_codewords * 280
+            return out
+
+        for _ in range(max(args.warmup, 1)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        consumed = 0
+        for _ in range(args.steps):
+            e2e_step()
+            consumed += eng2.last_samples
+        dt = time.perf_counter() - t0
+        barrier()
+        dt = max_over_ranks(dt)
+        consumed = sum_over_ranks(float(consumed))
+        e2e = {"value": round(consumed / dt / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(n * ec * 8),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": round(1e3 * dt / args.steps, 3),
+               "api": "wb_feed_strided(pinned host) + wb_process + wb_sync + wb_drain_all_packets"}
+        eng2.close()
+        del pin
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(8 << 20)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(l1 - l0),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "work_per_step_per_gpu": {"samples": int(samples_step), "codewords": int(codewords_step),
+                                      "crc_valid_packets": packets_last},
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -168,8 +168,8 @@ uint64_t wb_last_samples(wb_engine *e);
 /* pinned host memory for staging buffers handed to wb_feed / wb_feed_strided */
 void *wb_host_alloc(size_t bytes);
 void  wb_host_free(void *p);
-/* derived geometry: out[0..11] = N, Nbits, Ts, P, Ndft, nmax, job_cap, sd_cap, Nsym, M, ldpc_max_iter,
-   symbols collected per packet */
+/* derived geometry: out[0..13] = N, Nbits, Ts, P, Ndft, nmax, job_cap, sd_cap, Nsym, M, ldpc_max_iter,
+   symbols collected per packet, streams per CTA and shared-memory bytes per CTA of the demodulator kernel */
 int  wb_geometry(wb_engine *e, int32_t *out, int n);
 /* test tap: log {nin, f_est bins[4], norm_rx_timing, ppm, rx_timing} of the first frames_per_stream frames of
    each following wb_process (what oracle/ref_harness.c logs per frame of src/fsk_demod.c:270-299) */

@@ -19,7 +19,6 @@
 #include <string.h>
 
 #include <algorithm>
-#include <deque>
 #include <vector>
 
 #include "wb_internal.h"
@@ -90,7 +89,9 @@ struct wb_engine {
     std::vector<wb_cursor> cursor;                 /* as of the last wb_sync */
     std::vector<unsigned long long> fill;          /* samples resident per stream (host's view) */
     std::vector<int> nin;
-    std::vector<std::deque<uint8_t>> packets;      /* CRC-valid payloads not yet drained, per stream */
+    struct pktq { std::vector<uint8_t> buf; size_t rd = 0; size_t size() const { return buf.size() - rd; }
+                  void clear() { buf.clear(); rd = 0; } };
+    std::vector<pktq> packets;                     /* CRC-valid payloads not yet drained, per stream */
     std::vector<wb_codeword> last_cw;              /* codewords of the last wb_process, (stream, seq) order */
     std::vector<float> last_llr;
     bool uniform_fill;                             /* every stream has the same fill (strided feed possible) */
@@ -100,6 +101,7 @@ struct wb_engine {
     uint64_t last_codewords, last_samples;
     float kernel_ms[4];
     size_t fsk_smem;
+    int spb;
 };
 
 /* ---- table construction ------------------------------------------------- */
@@ -194,10 +196,11 @@ static int build_fsk_params(const wb_config *cfg, wb_fsk_params *fp)
     default: return wb_fail(WB_EINVAL, "unknown in_fmt %d", cfg->in_fmt);
     }
     fp->xlen = (fp->nstash + fp->nmax + 1) & ~1;
-    fp->blen = std::max((M - 1) * fp->nint, Ndft);
-    int bytes = (fp->xlen + fp->blen) * 8;
-    fp->sreg = ((bytes + 127 - 8) / 128) * 128 + 8;            /* == 8 (mod 128), >= bytes */
-    if (fp->sreg < bytes) fp->sreg += 128;
+    fp->ylen = (fp->nsteps + 1) & ~1;
+    fp->blen = std::max((M - 1) * fp->ylen, Ndft);
+    int bytes = (fp->xlen + fp->blen) * 8 + ((fp->nint * 4 + 7) & ~7);
+    fp->sreg = (bytes & ~15) + 8;                              /* == 8 (mod 16): lanes of warp 0 hit distinct banks */
+    if (fp->sreg < bytes) fp->sreg += 16;
     return WB_OK;
 }
 
@@ -348,10 +351,12 @@ static int init_states(wb_engine *e)
     return WB_OK;
 }
 
-template <int M, int TS>
+template <int M, int TS, bool CF32>
 static cudaError_t fsk_set_attr(size_t smem)
 {
-    return cudaFuncSetAttribute(wb_fsk_kernel<M, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t ce = cudaFuncSetAttribute(wb_fsk_kernel<M, TS, CF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return ce;
+    return cudaFuncSetAttribute(wb_fsk_kernel<M, TS, CF32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 }
 
 extern "C" int wb_create(const wb_config *cfg, wb_engine **out)
@@ -439,15 +444,28 @@ extern "C" int wb_create(const wb_config *cfg, wb_engine **out)
     if (rc) { wb_destroy(e); return rc; }
     rc = init_states(e);
     if (rc) { wb_destroy(e); return rc; }
-    /* kernel attributes */
+    /* kernel attributes: streams per CTA so that two CTAs share an SM (one in a sequential phase while the
+       other runs a parallel one) */
     {
-        const int SPB = 32 / e->fp.M;
-        e->fsk_smem = ((sizeof(wb_fsk_sc) * SPB + 127) / 128) * 128 + (size_t)SPB * e->fp.sreg;
+        const int max_spb = (e->fp.M == 2) ? 14 : 8;           /* launch bounds of wb_fsk_kernel */
+        int dev_smem_sm = 0, dev_smem_blk = 0;
+        CRE(cudaDeviceGetAttribute(&dev_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cfg->device));
+        CRE(cudaDeviceGetAttribute(&dev_smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
+        auto smem_for = [&](int spb) { return ((sizeof(wb_fsk_sc) * spb + 127) / 128) * 128 + (size_t)spb * e->fp.sreg; };
+        int spb = 0;
+        for (int ctas = 2; ctas >= 1 && spb == 0; ctas--)
+            for (int t = max_spb; t >= (ctas == 2 ? 4 : 1); t--)
+                if (smem_for(t) <= (size_t)dev_smem_blk && ctas * (smem_for(t) + 1024) <= (size_t)dev_smem_sm) { spb = t; break; }
+        if (spb == 0) { wb_destroy(e); return wb_fail(WB_EINVAL, "FSK kernel does not fit shared memory"); }
+        if (getenv("WB_FSK_SPB")) spb = std::max(1, std::min(max_spb, atoi(getenv("WB_FSK_SPB"))));
+        e->spb = spb;
+        e->fsk_smem = smem_for(spb);
+        const bool cf32 = e->fp.in_fmt == WB_FMT_CF32;
         cudaError_t ce = cudaErrorInvalidValue;
-        if (e->fp.M == 2 && e->fp.Ts == 8) ce = fsk_set_attr<2, 8>(e->fsk_smem);
-        else if (e->fp.M == 2 && e->fp.Ts == 10) ce = fsk_set_attr<2, 10>(e->fsk_smem);
-        else if (e->fp.M == 4 && e->fp.Ts == 8) ce = fsk_set_attr<4, 8>(e->fsk_smem);
-        else if (e->fp.M == 4 && e->fp.Ts == 10) ce = fsk_set_attr<4, 10>(e->fsk_smem);
+        if (e->fp.M == 2 && e->fp.Ts == 8) ce = cf32 ? fsk_set_attr<2, 8, true>(e->fsk_smem) : fsk_set_attr<2, 8, false>(e->fsk_smem);
+        else if (e->fp.M == 2 && e->fp.Ts == 10) ce = cf32 ? fsk_set_attr<2, 10, true>(e->fsk_smem) : fsk_set_attr<2, 10, false>(e->fsk_smem);
+        else if (e->fp.M == 4 && e->fp.Ts == 8) ce = cf32 ? fsk_set_attr<4, 8, true>(e->fsk_smem) : fsk_set_attr<4, 8, false>(e->fsk_smem);
+        else if (e->fp.M == 4 && e->fp.Ts == 10) ce = cf32 ? fsk_set_attr<4, 10, true>(e->fsk_smem) : fsk_set_attr<4, 10, false>(e->fsk_smem);
         else { wb_destroy(e); return wb_fail(WB_EINVAL, "Fs/Rs = %d: only 8 and 10 samples per symbol are built", e->fp.Ts); }
         if (ce != cudaSuccess) { wb_fail(WB_ECUDA, "fsk kernel smem %zu: %s", e->fsk_smem, cudaGetErrorString(ce)); wb_destroy(e); return WB_ECUDA; }
         CRE(cudaFuncSetAttribute(wb_ldpc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(wb_ldpc_smem)));
@@ -558,15 +576,16 @@ __global__ void wb_gather_kernel(const wb_codeword *cw, const float *llr, const 
 template <int M, int TS>
 static void launch_fsk(wb_engine *e, const wb_fsk_args &a)
 {
-    const int SPB = 32 / M;
-    int grid = (e->cfg.n_streams + SPB - 1) / SPB;
-    wb_fsk_kernel<M, TS><<<grid, SPB * 32, e->fsk_smem, e->stream>>>(e->fp, a);
+    const int grid = (e->cfg.n_streams + e->spb - 1) / e->spb;
+    if (e->fp.in_fmt == WB_FMT_CF32) wb_fsk_kernel<M, TS, true><<<grid, e->spb * 32, e->fsk_smem, e->stream>>>(e->fp, a);
+    else wb_fsk_kernel<M, TS, false><<<grid, e->spb * 32, e->fsk_smem, e->stream>>>(e->fp, a);
 }
 
 extern "C" int wb_process(wb_engine *e)
 {
     if (!e) return wb_fail(WB_EINVAL, "null engine");
-    int rc = wb_collect(e);
+    /* resident (benchmark) mode queues passes back to back: only the last one's records are collected */
+    int rc = e->resident_mode ? WB_OK : wb_collect(e);
     if (rc) return rc;
     CU(cudaSetDevice(e->cfg.device));
     const int n = e->cfg.n_streams;
@@ -580,7 +599,7 @@ extern "C" int wb_process(wb_engine *e)
     wb_fsk_args a;
     a.state = e->d_state; a.cursor = e->d_cursor; a.in = e->d_in; a.in_stride = e->in_stride;
     a.sd = e->d_sd; a.sd_stride = e->sd_stride; a.sd_cap = e->sd_cap; a.n_streams = n;
-    a.compact = e->resident_mode ? 0 : 1; a.headroom = WB_HEADROOM;
+    a.compact = e->resident_mode ? 0 : 1; a.headroom = WB_HEADROOM; a.spb = e->spb;
     a.frame_log = e->d_frame_log; a.log_cap = e->log_cap;
     CU(cudaEventRecord(e->ev[0], e->stream));
     if (e->fp.M == 2 && e->fp.Ts == 8) launch_fsk<2, 8>(e, a);
@@ -655,7 +674,7 @@ static int wb_collect(wb_engine *e)
         CU(cudaStreamSynchronize(e->stream));
         for (size_t i = 0; i < total; i++) {
             const wb_codeword &c = e->last_cw[i];
-            if (c.crc_ok) e->packets[c.stream].insert(e->packets[c.stream].end(), c.bytes, c.bytes + WB_PACKET_BYTES);
+            if (c.crc_ok) { auto &q = e->packets[c.stream].buf; q.insert(q.end(), c.bytes, c.bytes + WB_PACKET_BYTES); }
         }
     }
     return WB_OK;
@@ -676,11 +695,12 @@ extern "C" int wb_drain_packets(wb_engine *e, int stream, uint8_t *buf, size_t c
     if (stream < 0 || stream >= e->cfg.n_streams) return wb_fail(WB_EINVAL, "stream %d out of range", stream);
     int rc = wb_collect(e);
     if (rc) return rc;
-    std::deque<uint8_t> &q = e->packets[stream];
+    wb_engine::pktq &q = e->packets[stream];
     size_t n = std::min(q.size(), cap - cap % WB_PACKET_BYTES);
     if (n && !buf) return wb_fail(WB_EINVAL, "null buffer");
-    std::copy(q.begin(), q.begin() + n, buf);
-    q.erase(q.begin(), q.begin() + n);
+    if (n) memcpy(buf, q.buf.data() + q.rd, n);
+    q.rd += n;
+    if (q.rd == q.buf.size()) q.clear();
     *nbytes = n;
     return WB_OK;
 }
@@ -696,15 +716,16 @@ extern "C" int wb_drain_all_packets(wb_engine *e, uint8_t *buf, size_t cap, size
     if (need > cap) { *nbytes = need; return wb_fail(WB_ERANGE, "need %zu bytes", need); }
     size_t o = 0; uint64_t np = 0;
     for (int s = 0; s < e->cfg.n_streams; s++) {
-        std::deque<uint8_t> &q = e->packets[s];
+        wb_engine::pktq &q = e->packets[s];
         uint32_t k = 0;
         while (q.size() >= WB_PACKET_BYTES) {
             int32_t ss = s;
             memcpy(buf + o, &ss, 4); memcpy(buf + o + 4, &k, 4);
-            std::copy(q.begin(), q.begin() + WB_PACKET_BYTES, buf + o + 8);
-            q.erase(q.begin(), q.begin() + WB_PACKET_BYTES);
+            memcpy(buf + o + 8, q.buf.data() + q.rd, WB_PACKET_BYTES);
+            q.rd += WB_PACKET_BYTES;
             o += rec; k++; np++;
         }
+        q.clear();
     }
     *nbytes = o;
     if (npackets) *npackets = np;
@@ -877,7 +898,7 @@ __global__ void wb_rewind_kernel(wb_stream_state *st, int n, unsigned headroom, 
 extern "C" int wb_dev_set_fill(wb_engine *e, uint64_t nsamp)
 {
     if (!e) return wb_fail(WB_EINVAL, "null engine");
-    int rc = wb_collect(e);
+    int rc = e->resident_mode ? WB_OK : wb_collect(e);
     if (rc) return rc;
     if (nsamp > e->cfg.chunk_samples) return wb_fail(WB_ERANGE, "nsamp exceeds chunk_samples");
     CU(cudaSetDevice(e->cfg.device));
@@ -1060,8 +1081,8 @@ extern "C" void wb_host_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" int wb_geometry(wb_engine *e, int32_t *out, int n)
 {
     if (!e || !out) return wb_fail(WB_EINVAL, "null argument");
-    int32_t g[12] = {e->fp.N, e->fp.Nbits, e->fp.Ts, e->fp.P, e->fp.Ndft, e->fp.nmax, e->job_cap, (int32_t)e->sd_cap,
-                     e->fp.Nsym, e->fp.M, e->max_iter, e->dp.nsym};
-    for (int i = 0; i < n && i < 12; i++) out[i] = g[i];
+    int32_t g[14] = {e->fp.N, e->fp.Nbits, e->fp.Ts, e->fp.P, e->fp.Ndft, e->fp.nmax, e->job_cap, (int32_t)e->sd_cap,
+                     e->fp.Nsym, e->fp.M, e->max_iter, e->dp.nsym, e->spb, (int32_t)e->fsk_smem};
+    for (int i = 0; i < n && i < 14; i++) out[i] = g[i];
     return WB_OK;
 }

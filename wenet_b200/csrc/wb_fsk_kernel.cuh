@@ -12,27 +12,33 @@
  * the nin sequence and the estimator state are bit-identical to the CPU pipe.
  *
  * Mapping.  Frames of one stream are strictly sequential (nin of frame k+1 comes out of frame k),
- * and inside a frame the tone oscillators (phi_c *= dphi, 399 dependent complex products per tone)
- * and the fine-timing accumulator (392 dependent additions) are sequential too.  So:
+ * and inside a frame two recurrences are sequential as well: the tone oscillators
+ * (phi_c *= dphi, Nmem-1 dependent complex products per tone) and the fine-timing accumulator
+ * (nint dependent additions).  Everything else is parallel over the sample index.  So:
  *
- *   CTA = SPB = 32/M streams, one "stream warp" per stream, frames in lock step.
- *   phase A (stream warps, lanes = samples / butterflies / bins):
- *           land the prefetched frame in shared memory, issue the prefetch of the next one
- *           (global loads into registers, consumed a whole frame later: HBM latency is off the
- *           critical path), window + 256-point FFT in the reference's butterfly order, spectrum IIR
- *           (kept in registers), warp-argmax peak picking.
- *   phase B (warp 0, lane = (tone, stream)): ALL the sequential work of the CTA's streams at once:
- *           oscillator recurrence, down-mix, Ts-tap ring buffer in registers, integrator output,
- *           |.|^2 summed over tones by shuffle, fine-timing accumulation (real part on the tone-0
- *           lane, imaginary part on the tone-1 lane), then atan2 / ppm / nin on the tone-0 lanes.
- *           32 dependent chains share every issue slot instead of one chain idling 31 lanes.
- *   phase C (stream warps, lanes = symbols): linear-interpolated resampling and soft decisions,
- *           48 (96) floats per frame written coalesced.
+ *   CTA = spb streams (runtime; 14 for 2-FSK at Ts = 8 so that two CTAs = 28 streams fit one SM and
+ *   4096 streams are all resident on 148 SMs), one "stream warp" per stream, frames in lock step.
  *
- * Shared memory per stream: x[nstash + nmax] float2 (old + new samples; overwritten in place by tone
- * 0's integrator outputs, which trail the read pointer) and (M-1) * nint float2 for the other tones
- * (doubling as the FFT work buffer in phase A).  Stream regions are 8 bytes mod 128 apart so the 16
- * streams read by a half-warp in phase B fall in distinct banks.
+ *   A  (stream warps)  land the prefetched frame in shared memory, window + 256-point FFT in the
+ *                      reference's butterfly order, spectrum IIR (registers), warp-argmax peak
+ *                      picking, then issue the global loads of the NEXT frame into registers
+ *                      (consumed a whole frame later: HBM latency is off the critical path).
+ *   B1 (warp 0, lane = (tone, stream))  ONLY the sequential part of the mixer: oscillator
+ *                      recurrence + down-mix product, written in place over the samples.
+ *   B2 (stream warps, lanes = integrator outputs)  Ts-tap sums in the reference's ring-buffer slot
+ *                      order, in place; |.|^2 summed over tones -> e[i].
+ *   B3 (warp 0, lane = (re/im, stream))  the sequential fine-timing accumulation over e[i], then
+ *                      atan2 / ppm / nin / resampling offsets on the re-lanes.
+ *   C  (stream warps, lanes = symbols)  linear-interpolated resampling and soft decisions,
+ *                      48 (96) floats per frame written coalesced.
+ *
+ * The sequential phases cost one warp's issue slots for ALL streams of the CTA (every lane carries
+ * a different dependent chain); while one CTA of an SM is in B1/B3 the other one runs A/B2/C.
+ *
+ * Shared memory per stream: X[nstash + nmax] float2 (old + new samples -> tone 0 mixer products ->
+ * tone 0 integrator outputs, all in place), Y[(M-1) * ylen] float2 for the other tones (the FFT work
+ * buffer in phase A) and E[nint] floats.  Stream regions are an odd multiple of 8 bytes mod 128
+ * apart so the lanes of warp 0 (one stream each) hit distinct banks.
  * HBM traffic: every input sample is read once (8 B as cf32), 4 B x Nbits/N written.
  */
 #ifndef WB_FSK_KERNEL_CUH
@@ -41,18 +47,16 @@
 #include "wb_internal.h"
 #include "wb_math.h"
 
-#define WB_NPRE (WB_MAX_NIN / 32)
 #define WB_NST ((WB_MAX_NSTASH + 31) / 32)
 #define WB_NEQ (WB_MAX_NDFT / 2 / 32)
 
-struct wb_fsk_sc {                 /* per-stream frame scalars in shared memory */
+struct wb_fsk_sc {                 /* per-stream frame scalars in shared memory (88 bytes) */
     float2 phi_c[WB_MAXM];
-    int pb[WB_MAXM];               /* estimator bins in force before this frame (fsk->f_est) */
-    int nb[WB_MAXM];               /* bins estimated from this frame */
-    int nin, active, nin_next, nanflag;
+    short pb[WB_MAXM];             /* estimator bins in force before this frame (fsk->f_est) */
+    short nb[WB_MAXM];             /* bins estimated from this frame */
+    int nin, flags, nin_next;      /* flags: bit 0 = active this frame, bit 1 = NaN guard tripped */
     int low, high;
     float fract, norm, ppm, rx_timing;
-    float ebno_db, snr_est;
 };
 
 struct wb_fsk_args {
@@ -64,6 +68,7 @@ struct wb_fsk_args {
     unsigned long long sd_stride;
     unsigned sd_cap;               /* floats available after WB_CARRY_CAP */
     int n_streams;
+    int spb;                       /* streams per CTA = warps per CTA */
     int compact;                   /* park the unconsumed remainder right before the headroom mark */
     unsigned headroom;             /* samples; wb_feed appends at this row offset after a compacting process */
     float *frame_log;              /* optional test tap [n_streams][log_cap][8] */
@@ -79,93 +84,109 @@ __device__ __forceinline__ float2 wb_cmul2(float2 a, float2 b)   /* reference sr
 }
 
 /* raw sample -> COMP, reference src/fsk_demod.c:273-296 */
-__device__ __forceinline__ float2 wb_convert(int fmt, uint2 raw)
+template <bool CF32>
+__device__ __forceinline__ float2 wb_convert(int fmt, unsigned lo, unsigned hi)
 {
     float2 v;
-    if (fmt == WB_FMT_CF32) {
-        v.x = __uint_as_float(raw.x); v.y = __uint_as_float(raw.y);
+    if (CF32) {
+        v.x = __uint_as_float(lo); v.y = __uint_as_float(hi);
     } else if (fmt == WB_FMT_CU8) {
         /* ((float)u8 - 127.0) / 128.0 in double, then to float: exact, so float arithmetic gives the same */
-        v.x = __fmul_rn(__fsub_rn((float)(raw.x & 0xffu), 127.0f), 0.0078125f);
-        v.y = __fmul_rn(__fsub_rn((float)((raw.x >> 8) & 0xffu), 127.0f), 0.0078125f);
+        v.x = __fmul_rn(__fsub_rn((float)(lo & 0xffu), 127.0f), 0.0078125f);
+        v.y = __fmul_rn(__fsub_rn((float)((lo >> 8) & 0xffu), 127.0f), 0.0078125f);
     } else if (fmt == WB_FMT_CS16) {
-        v.x = __fdiv_rn((float)(short)(raw.x & 0xffffu), 1000.0f);
-        v.y = __fdiv_rn((float)(short)(raw.x >> 16), 1000.0f);
+        v.x = __fdiv_rn((float)(short)(lo & 0xffffu), 1000.0f);
+        v.y = __fdiv_rn((float)(short)(lo >> 16), 1000.0f);
     } else {
-        v.x = __fdiv_rn((float)(short)(raw.x & 0xffffu), 1000.0f);
+        v.x = __fdiv_rn((float)(short)(lo & 0xffffu), 1000.0f);
         v.y = 0.0f;
     }
     return v;
 }
 
-__device__ __forceinline__ uint2 wb_load_raw(int fmt, const unsigned char *p, unsigned long long idx)
+template <bool CF32>
+__device__ __forceinline__ void wb_load_raw(int fmt, const unsigned char *p, unsigned long long idx, unsigned &lo, unsigned &hi)
 {
-    uint2 r = make_uint2(0u, 0u);
-    if (fmt == WB_FMT_CF32) {
-        r = __ldg(reinterpret_cast<const uint2 *>(p) + idx);
+    if (CF32) {
+        uint2 r = __ldg(reinterpret_cast<const uint2 *>(p) + idx);
+        lo = r.x; hi = r.y;
     } else if (fmt == WB_FMT_CS16) {
-        r.x = __ldg(reinterpret_cast<const unsigned *>(p) + idx);
+        lo = __ldg(reinterpret_cast<const unsigned *>(p) + idx); hi = 0u;
     } else {
-        r.x = __ldg(reinterpret_cast<const unsigned short *>(p) + idx);
+        lo = __ldg(reinterpret_cast<const unsigned short *>(p) + idx); hi = 0u;
     }
-    return r;
 }
 
-template <int M, int TS>
-__global__ void __launch_bounds__(32 / M * 32)
+/* one mixer step: product with the conjugated oscillator (reference src/fsk.c:794-798) */
+#define WB_MIX_STEP(SRC, DST, N)                                                            \
+    do {                                                                                    \
+        const float2 x_ = (SRC)[N];                                                         \
+        float2 o_;                                                                          \
+        o_.x = __fadd_rn(__fmul_rn(x_.x, ph.x), __fmul_rn(x_.y, ph.y));                     \
+        o_.y = __fsub_rn(__fmul_rn(x_.y, ph.x), __fmul_rn(x_.x, ph.y));                     \
+        (DST)[N] = o_;                                                                      \
+        ph = wb_cmul2(ph, d);                                                               \
+    } while (0)
+
+template <int M, int TS, bool CF32>
+__global__ void __launch_bounds__(M == 2 ? 448 : 256, 2)
 wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 {
-    constexpr int SPB = 32 / M;
+    constexpr int NPRE = (TS * WB_FRAME_SYMS + TS / 2 + 31) / 32;     /* lanes x NPRE >= nmax */
     extern __shared__ __align__(16) unsigned char wb_fsk_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int sg = blockIdx.x * SPB + warp;
+    const int spb = a.spb;
+    const int sg = blockIdx.x * spb + warp;
     const bool have = sg < a.n_streams;
 
     wb_fsk_sc *sc = reinterpret_cast<wb_fsk_sc *>(wb_fsk_raw);
-    unsigned char *regions = wb_fsk_raw + ((sizeof(wb_fsk_sc) * SPB + 127) / 128) * 128;
-    float2 *xbuf = reinterpret_cast<float2 *>(regions + (size_t)warp * p.sreg);
-    float2 *bbuf = xbuf + p.xlen;
+    unsigned char *regions = wb_fsk_raw + ((sizeof(wb_fsk_sc) * spb + 127) / 128) * 128;
+    float2 *X = reinterpret_cast<float2 *>(regions + (size_t)warp * p.sreg);
+    float2 *Y = X + p.xlen;
+    float *E = reinterpret_cast<float *>(Y + p.blen);
     const int Ndft = p.Ndft, nh = Ndft >> 1, nstash = p.nstash, fmt = p.in_fmt;
 
     /* ---- per-stream state -> registers / shared memory ---- */
     wb_stream_state *st = have ? a.state + sg : nullptr;
     const unsigned char *in = a.in + (size_t)(have ? sg : 0) * a.in_stride;
     float *sdrow = a.sd + (size_t)(have ? sg : 0) * a.sd_stride + WB_CARRY_CAP;
-    unsigned long long pos = 0, fill = 0, pos0 = 0, frames = 0;
+    unsigned long long pos = 0, fill = 0, pos0 = 0;
+    unsigned frames = 0;
     int nin = p.N;
     unsigned n_out = 0;
     float est[WB_NEQ];
     float2 stash[WB_NST];
-    uint2 pre[WB_NPRE];
+    unsigned pre_lo[NPRE], pre_hi[NPRE];
 #pragma unroll
     for (int q = 0; q < WB_NEQ; q++) est[q] = 0.0f;
 #pragma unroll
     for (int q = 0; q < WB_NST; q++) stash[q] = make_float2(0.0f, 0.0f);
     if (have) {
-        pos = pos0 = st->in_pos; fill = st->in_fill; nin = st->nin; frames = st->frames;
+        pos = pos0 = st->in_pos; fill = st->in_fill; nin = st->nin;
 #pragma unroll
         for (int q = 0; q < WB_NEQ; q++)
             if (lane + 32 * q < nh) est[q] = st->fft_est[lane + 32 * q];
 #pragma unroll
         for (int q = 0; q < WB_NST; q++)
-            if (lane + 32 * q < nstash) xbuf[lane + 32 * q] = st->samp_old[lane + 32 * q];
+            if (lane + 32 * q < nstash) X[lane + 32 * q] = st->samp_old[lane + 32 * q];
         if (lane == 0) {
             wb_fsk_sc &c = sc[warp];
-            for (int m = 0; m < M; m++) { c.phi_c[m] = st->phi_c[m]; c.pb[m] = st->fbin[m]; c.nb[m] = 0; }
+            for (int m = 0; m < M; m++) { c.phi_c[m] = st->phi_c[m]; c.pb[m] = (short)st->fbin[m]; c.nb[m] = 0; }
             c.norm = st->norm_rx_timing; c.ppm = st->ppm; c.rx_timing = st->rx_timing;
-            c.nin = nin; c.nin_next = nin; c.active = 0; c.nanflag = 0;
-            c.ebno_db = 0.0f; c.snr_est = 0.0f;
+            c.nin = nin; c.nin_next = nin; c.flags = 0; c.low = c.high = 0; c.fract = 0.0f;
         }
     } else if (lane == 0) {
         wb_fsk_sc &c = sc[warp];
         for (int m = 0; m < M; m++) { c.phi_c[m] = make_float2(1.0f, 0.0f); c.pb[m] = 0; c.nb[m] = 0; }
-        c.nin = p.N; c.active = 0; c.nin_next = p.N; c.nanflag = 0; c.norm = 0.0f; c.ppm = 0.0f;
+        c.nin = p.N; c.flags = 0; c.nin_next = p.N; c.norm = 0.0f; c.ppm = 0.0f; c.rx_timing = 0.0f;
+        c.low = c.high = 0; c.fract = 0.0f;
     }
     /* prefetch the first frame */
 #pragma unroll
-    for (int q = 0; q < WB_NPRE; q++) {
-        int n = lane + 32 * q;
-        pre[q] = (have && n < p.nmax && pos + n < fill) ? wb_load_raw(fmt, in, pos + n) : make_uint2(0u, 0u);
+    for (int q = 0; q < NPRE; q++) {
+        const int n = lane + 32 * q;
+        pre_lo[q] = pre_hi[q] = 0u;
+        if (have && n < p.nmax && pos + n < fill) wb_load_raw<CF32>(fmt, in, pos + n, pre_lo[q], pre_hi[q]);
     }
 
     const float omt = __fsub_rn(1.0f, p.tc);
@@ -173,31 +194,27 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     for (;;) {
         const bool active = have && (pos + (unsigned long long)nin <= fill) && (n_out + (unsigned)p.Nbits <= a.sd_cap);
         if (!__syncthreads_or(active)) break;
-        unsigned long long pos_next = pos + nin;
+        const unsigned long long pos_next = pos + nin;
+        const int xo = nstash - (p.Nmem - nin);      /* X index of the first mixer sample */
 
-        /* ================= phase A: stream warps ================= */
+        /* ================= A: stream warps ================= */
         if (active) {
 #pragma unroll
-            for (int q = 0; q < WB_NPRE; q++) {
-                int n = lane + 32 * q;
-                if (n < p.nmax) xbuf[nstash + n] = wb_convert(fmt, pre[q]);
-            }
-#pragma unroll
-            for (int q = 0; q < WB_NPRE; q++) {
-                int n = lane + 32 * q;
-                pre[q] = (n < p.nmax && pos_next + n < fill) ? wb_load_raw(fmt, in, pos_next + n) : make_uint2(0u, 0u);
+            for (int q = 0; q < NPRE; q++) {
+                const int n = lane + 32 * q;
+                if (n < p.nmax) X[nstash + n] = wb_convert<CF32>(fmt, pre_lo[q], pre_hi[q]);
             }
             __syncwarp();
             /* window the first nin - Ndft samples, zero-pad, in the leaf order of the DIT recursion
                (reference src/fsk.c:583-603, src/kiss_fft.c:238-306) */
             const int nwin = min(nin - Ndft, Ndft);
-            float2 *F = bbuf;
+            float2 *F = Y;
             for (int o = lane; o < Ndft; o += 32) {
-                int idx = __ldg(&p.perm[o]);
+                const int idx = __ldg(&p.perm[o]);
                 float2 v = make_float2(0.0f, 0.0f);
                 if (idx < nwin) {
-                    float h = __ldg(&p.hann[idx]);
-                    float2 x = xbuf[nstash + idx];
+                    const float h = __ldg(&p.hann[idx]);
+                    const float2 x = X[nstash + idx];
                     v.x = __fmul_rn(h, x.x); v.y = __fmul_rn(h, x.y);
                 }
                 F[o] = v;
@@ -207,24 +224,24 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 const int pp = p.lev_p[L], mm = p.lev_m[L], fs = p.lev_fstride[L];
                 const int nbf = Ndft / pp;
                 for (int t = lane; t < nbf; t += 32) {
-                    int blk = t / mm, k = t - blk * mm;
-                    int base = blk * pp * mm + k;
+                    const int blk = t / mm, k = t - blk * mm;
+                    const int base = blk * pp * mm + k;
                     if (pp == 4) {      /* reference src/kiss_fft.c:44-90, forward */
-                        float2 f0 = F[base], f1 = F[base + mm], f2 = F[base + 2 * mm], f3 = F[base + 3 * mm];
-                        float2 s0 = wb_cmul2(f1, __ldg(&p.tw[k * fs]));
-                        float2 s1 = wb_cmul2(f2, __ldg(&p.tw[2 * k * fs]));
-                        float2 s2 = wb_cmul2(f3, __ldg(&p.tw[3 * k * fs]));
-                        float2 s5 = make_float2(__fsub_rn(f0.x, s1.x), __fsub_rn(f0.y, s1.y));
-                        float2 aa = make_float2(__fadd_rn(f0.x, s1.x), __fadd_rn(f0.y, s1.y));
-                        float2 s3 = make_float2(__fadd_rn(s0.x, s2.x), __fadd_rn(s0.y, s2.y));
-                        float2 s4 = make_float2(__fsub_rn(s0.x, s2.x), __fsub_rn(s0.y, s2.y));
+                        const float2 f0 = F[base], f1 = F[base + mm], f2 = F[base + 2 * mm], f3 = F[base + 3 * mm];
+                        const float2 s0 = wb_cmul2(f1, __ldg(&p.tw[k * fs]));
+                        const float2 s1 = wb_cmul2(f2, __ldg(&p.tw[2 * k * fs]));
+                        const float2 s2 = wb_cmul2(f3, __ldg(&p.tw[3 * k * fs]));
+                        const float2 s5 = make_float2(__fsub_rn(f0.x, s1.x), __fsub_rn(f0.y, s1.y));
+                        const float2 aa = make_float2(__fadd_rn(f0.x, s1.x), __fadd_rn(f0.y, s1.y));
+                        const float2 s3 = make_float2(__fadd_rn(s0.x, s2.x), __fadd_rn(s0.y, s2.y));
+                        const float2 s4 = make_float2(__fsub_rn(s0.x, s2.x), __fsub_rn(s0.y, s2.y));
                         F[base + 2 * mm] = make_float2(__fsub_rn(aa.x, s3.x), __fsub_rn(aa.y, s3.y));
                         F[base] = make_float2(__fadd_rn(aa.x, s3.x), __fadd_rn(aa.y, s3.y));
                         F[base + mm] = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));
                         F[base + 3 * mm] = make_float2(__fsub_rn(s5.x, s4.y), __fadd_rn(s5.y, s4.x));
                     } else {            /* reference src/kiss_fft.c:22-42 */
-                        float2 f0 = F[base], f1 = F[base + mm];
-                        float2 tt = wb_cmul2(f1, __ldg(&p.tw[k * fs]));
+                        const float2 f0 = F[base], f1 = F[base + mm];
+                        const float2 tt = wb_cmul2(f1, __ldg(&p.tw[k * fs]));
                         F[base + mm] = make_float2(__fsub_rn(f0.x, tt.x), __fsub_rn(f0.y, tt.y));
                         F[base] = make_float2(__fadd_rn(f0.x, tt.x), __fadd_rn(f0.y, tt.y));
                     }
@@ -235,11 +252,11 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             float v[WB_NEQ];
 #pragma unroll
             for (int q = 0; q < WB_NEQ; q++) {
-                int i = lane + 32 * q;
+                const int i = lane + 32 * q;
                 v[q] = 0.0f;
                 if (i < nh) {
-                    float2 X = F[i];
-                    float pw = __fadd_rn(__fmul_rn(X.x, X.x), __fmul_rn(X.y, X.y));
+                    const float2 Xf = F[i];
+                    float pw = __fadd_rn(__fmul_rn(Xf.x, Xf.x), __fmul_rn(Xf.y, Xf.y));
                     if (i < p.f_min || i >= p.f_max - 1) pw = 0.0f;
                     est[q] = __fadd_rn(__fmul_rn(est[q], omt), __fmul_rn(__fsqrt_rn(pw), p.tc));
                     v[q] = est[q];
@@ -255,14 +272,14 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                     if (lane + 32 * q < nh && v[q] > bv) { bv = v[q]; bi = lane + 32 * q; }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
-                    float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                     if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
                 }
-                int lo = max(bi - p.f_zero, 0), hi = min(bi + p.f_zero, Ndft);
+                const int lo = max(bi - p.f_zero, 0), hi = min(bi + p.f_zero, Ndft);
 #pragma unroll
                 for (int q = 0; q < WB_NEQ; q++) {
-                    int i = lane + 32 * q;
+                    const int i = lane + 32 * q;
                     if (i >= lo && i < hi) v[q] = 0.0f;
                 }
                 freqi[m] = bi;
@@ -271,90 +288,145 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             for (int i = 1; i < M; i++) {       /* insertion sort, M <= 4 */
 #pragma unroll
                 for (int j = i; j > 0; j--)
-                    if (freqi[j - 1] > freqi[j]) { int t = freqi[j]; freqi[j] = freqi[j - 1]; freqi[j - 1] = t; }
+                    if (freqi[j - 1] > freqi[j]) { const int t = freqi[j]; freqi[j] = freqi[j - 1]; freqi[j - 1] = t; }
             }
-            /* the samples to stash for the next frame (reference src/fsk.c:851) sit where tone 0's
-               integrator outputs are about to land: lift them into registers */
+            /* the samples to stash for the next frame (reference src/fsk.c:851) sit where the mixer
+               products are about to land: lift them into registers */
 #pragma unroll
             for (int q = 0; q < WB_NST; q++)
-                if (lane + 32 * q < nstash) stash[q] = xbuf[nin + lane + 32 * q];
+                if (lane + 32 * q < nstash) stash[q] = X[nin + lane + 32 * q];
             if (lane == 0) {
                 wb_fsk_sc &c = sc[warp];
                 const bool first = c.pb[0] == 0;         /* fsk->f_est[0] < 1, reference src/fsk.c:729 */
 #pragma unroll
-                for (int m = 0; m < M; m++) { c.nb[m] = freqi[m]; if (first) c.pb[m] = freqi[m]; }
-                c.nin = nin; c.active = 1;
+                for (int m = 0; m < M; m++) { c.nb[m] = (short)freqi[m]; if (first) c.pb[m] = (short)freqi[m]; }
+                c.nin = nin; c.flags = 1;
+            }
+            /* next frame: global loads now, consumed at the top of the next iteration */
+#pragma unroll
+            for (int q = 0; q < NPRE; q++) {
+                const int n = lane + 32 * q;
+                pre_lo[q] = pre_hi[q] = 0u;
+                if (n < p.nmax && pos_next + n < fill) wb_load_raw<CF32>(fmt, in, pos_next + n, pre_lo[q], pre_hi[q]);
             }
         } else if (lane == 0) {
-            sc[warp].active = 0;
+            sc[warp].flags = 0;
         }
         __syncthreads();
 
-        /* ================= phase B: warp 0, lane = (tone, stream) ================= */
-        if (warp == 0) {
-            const int m = lane / SPB, s = lane - m * SPB;
+        /* ================= B1: warp 0, lane = (tone, stream): oscillator + down-mix ================= */
+        if (warp == 0 && lane < M * spb) {
+            const int m = lane / spb, s = lane - m * spb;
             wb_fsk_sc &c = sc[s];
-            const int act = c.active;
-            const float2 *xs_base = reinterpret_cast<const float2 *>(regions + (size_t)s * p.sreg);
-            float2 *fo = (m == 0) ? const_cast<float2 *>(xs_base)
-                                  : const_cast<float2 *>(xs_base) + p.xlen + (m - 1) * p.nint;
-            const int fnin = c.nin, nold = p.Nmem - fnin;
-            const int nin_idx = (fnin < p.N) ? 0 : (fnin == p.N ? 1 : 2);
-            const int pb = c.pb[m], nbn = c.nb[m];
-            float2 ph = c.phi_c[m];
-            ph = wb_cmul2(__ldg(&p.back[nin_idx * nh + pb]), ph);     /* reference src/fsk.c:756-759 */
-            float2 d = __ldg(&p.dphi[pb]);
-            const float2 dnew = __ldg(&p.dphi[nbn]);
-            const float2 *xs = xs_base + (nstash - nold);
-            float2 ring[TS];
-#pragma unroll
-            for (int j = 0; j < TS; j++) ring[j] = make_float2(0.0f, 0.0f);
-            float acc = 0.0f;
-            int cnt = 0, iout = 0, n = 0;
-            const int nsteps = p.nsteps, step1 = p.step - 1;
+            if (c.flags & 1) {
+                float2 *Xs = reinterpret_cast<float2 *>(regions + (size_t)s * p.sreg);
+                const int fnin = c.nin, nold = p.Nmem - fnin;
+                const int nin_idx = (fnin < p.N) ? 0 : (fnin == p.N ? 1 : 2);
+                const int pb = c.pb[m], nbn = c.nb[m];
+                float2 ph = c.phi_c[m];
+                ph = wb_cmul2(__ldg(&p.back[nin_idx * nh + pb]), ph);     /* reference src/fsk.c:756-759 */
+                float2 d = __ldg(&p.dphi[pb]);
+                const float2 dnew = __ldg(&p.dphi[nbn]);
+                const float2 *src = Xs + (nstash - nold);
+                float2 *dst = (m == 0) ? Xs + (nstash - nold) : Xs + p.xlen + (m - 1) * p.ylen;
+                const int nsteps = p.nsteps;
+                const int nslow = 2 * p.Ts + p.Ts / 2 + 1;                /* > every possible nold */
+                int n = 0;
 #pragma unroll 1
-            for (int blk = 0; blk < p.Nsym + 2; blk++) {
+                for (; n < nslow; n++) {
+                    if (n == nold) {        /* old -> new samples: comp_normalize + new tone, src/fsk.c:787-788 */
+                        const float av = __fsqrt_rn(__fadd_rn(__fmul_rn(ph.x, ph.x), __fmul_rn(ph.y, ph.y)));
+                        ph.x = __fdiv_rn(ph.x, av); ph.y = __fdiv_rn(ph.y, av);
+                        d = dnew;
+                    }
+                    WB_MIX_STEP(src, dst, n);
+                }
+#pragma unroll 1
+                for (; n + 8 <= nsteps; n += 8) {
 #pragma unroll
-                for (int j = 0; j < TS; j++, n++) {
-                    if (n < nsteps) {
-                        if (n == nold) {        /* old -> new samples: comp_normalize + new tone, src/fsk.c:787-788 */
-                            float av = __fsqrt_rn(__fadd_rn(__fmul_rn(ph.x, ph.x), __fmul_rn(ph.y, ph.y)));
-                            ph.x = __fdiv_rn(ph.x, av); ph.y = __fdiv_rn(ph.y, av);
-                            d = dnew;
+                    for (int j = 0; j < 8; j++) WB_MIX_STEP(src + n, dst + n, j);
+                }
+#pragma unroll 1
+                for (; n < nsteps; n++) WB_MIX_STEP(src, dst, n);
+                c.phi_c[m] = ph;
+            }
+        }
+        __syncthreads();
+
+        /* ================= B2: stream warps, lanes = integrator outputs ================= */
+        if (active) {
+            /* f_int[m][i] = sum of the Ts ring-buffer slots after mixer step i*step + Ts - 1, added in slot
+               order (reference src/fsk.c:835-838): slot j holds the product of the step n in
+               [i*step, i*step + Ts) with n mod Ts == j.  In place: output i overwrites product i. */
+            const int step = p.step;
+            int r = (lane * step) % TS;                  /* (i * step) mod Ts for this lane's output */
+            const int rinc = (32 * step) % TS;
+            for (int i0 = 0; i0 < p.nint; i0 += 32) {
+                const int i = i0 + lane;
+                const bool valid = i < p.nint;
+                float2 f[M];
+                float e = 0.0f;
+                if (valid) {
+                    const int n0 = i * step;
+#pragma unroll
+                    for (int m = 0; m < M; m++) {
+                        const float2 *P = (m == 0) ? X + xo + n0 : Y + (m - 1) * p.ylen + n0;
+                        float sr = 0.0f, si = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < TS; j++) {
+                            int off = j - r;
+                            if (off < 0) off += TS;
+                            const float2 vv = P[off];
+                            if (j == 0) { sr = vv.x; si = vv.y; }
+                            else { sr = __fadd_rn(sr, vv.x); si = __fadd_rn(si, vv.y); }
                         }
-                        const float2 x = xs[n];
-                        /* cmult(sample, cconj(phi)), reference src/fsk.c:794 */
-                        ring[j].x = __fadd_rn(__fmul_rn(x.x, ph.x), __fmul_rn(x.y, ph.y));
-                        ring[j].y = __fsub_rn(__fmul_rn(x.y, ph.x), __fmul_rn(x.x, ph.y));
-                        ph = wb_cmul2(ph, d);
-                        if (n >= TS - 1) {
-                            if (cnt == 0) {
-                                cnt = step1;
-                                float sr = ring[0].x, si = ring[0].y;
-#pragma unroll
-                                for (int t = 1; t < TS; t++) { sr = __fadd_rn(sr, ring[t].x); si = __fadd_rn(si, ring[t].y); }
-                                if (act) fo[iout] = make_float2(sr, si);
-                                const float pw = __fadd_rn(__fmul_rn(sr, sr), __fmul_rn(si, si));
-                                float e = __shfl_sync(0xffffffffu, pw, s);
-#pragma unroll
-                                for (int mm = 1; mm < M; mm++) e = __fadd_rn(e, __shfl_sync(0xffffffffu, pw, mm * SPB + s));
-                                const float2 pf = __ldg(&p.pft[iout]);
-                                acc = __fadd_rn(acc, __fmul_rn(e, m == 0 ? pf.x : pf.y));
-                                iout++;
-                            } else {
-                                cnt--;
-                            }
-                        }
+                        f[m] = make_float2(sr, si);
+                        const float pw = __fadd_rn(__fmul_rn(sr, sr), __fmul_rn(si, si));
+                        e = (m == 0) ? pw : __fadd_rn(e, pw);        /* reference src/fsk.c:864-867 */
                     }
                 }
+                __syncwarp();
+                if (valid) {
+#pragma unroll
+                    for (int m = 0; m < M; m++) {
+                        float2 *P = (m == 0) ? X + xo : Y + (m - 1) * p.ylen;
+                        P[i] = f[m];
+                    }
+                    E[i] = e;
+                }
+                __syncwarp();
+                r += rinc;
+                if (r >= TS) r -= TS;
+            }
+        }
+        __syncthreads();
+
+        /* ================= B3: warp 0, lane = (re/im, stream): fine-timing accumulation ================= */
+        if (warp == 0) {
+            const int cidx = (lane < spb) ? 0 : 1;
+            const int s = min(lane - cidx * spb, spb - 1);
+            float acc = 0.0f;
+            if (lane < 2 * spb) {
+                const float *Es = reinterpret_cast<const float *>(
+                    reinterpret_cast<const float2 *>(regions + (size_t)s * p.sreg) + p.xlen + p.blen);
+                const float *pf = reinterpret_cast<const float *>(p.pft) + cidx;
+                int i = 0;
+#pragma unroll 1
+                for (; i + 8 <= p.nint; i += 8) {
+                    float ev[8], pv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { ev[j] = Es[i + j]; pv[j] = __ldg(pf + 2 * (i + j)); }
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc = __fadd_rn(acc, __fmul_rn(ev[j], pv[j]));   /* src/fsk.c:870 */
+                }
+                for (; i < p.nint; i++) acc = __fadd_rn(acc, __fmul_rn(Es[i], __ldg(pf + 2 * i)));
             }
             const float tcr = __shfl_sync(0xffffffffu, acc, s);
-            const float tci = __shfl_sync(0xffffffffu, acc, SPB + s);
-            if (act) {
-                c.phi_c[m] = ph;
-                if (m == 0) {
+            const float tci = __shfl_sync(0xffffffffu, acc, spb + s);
+            if (lane < spb) {
+                wb_fsk_sc &c = sc[s];
+                if (c.flags & 1) {
                     const bool nan = isnan(tcr) || isnan(tci);     /* reference src/fsk.c:878-880 */
-                    c.nanflag = nan;
                     if (!nan) {
                         const float norm = (float)((double)wb_atan2f(tci, tcr) / 6.283185307179586);
                         const float rx_timing = __fmul_rn(norm, (float)p.P);
@@ -373,18 +445,19 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                         c.high = (int)ceilf(rx_timing);
                         c.rx_timing = rx_timing;
                     } else {
-                        c.nin_next = fnin;
+                        c.flags = 3;
+                        c.nin_next = c.nin;
                     }
                 }
             }
         }
         __syncthreads();
 
-        /* ================= phase C: stream warps, lanes = symbols ================= */
+        /* ================= C: stream warps, lanes = symbols ================= */
         if (active) {
             wb_fsk_sc &c = sc[warp];
             float *out = sdrow + n_out;
-            if (!c.nanflag) {
+            if (!(c.flags & 2)) {
                 const int low = c.low, high = c.high;
                 const float fract = c.fract, omf = __fsub_rn(1.0f, fract);
                 for (int i = lane; i < p.Nsym; i += 32) {
@@ -392,7 +465,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                     float tm[M];
 #pragma unroll
                     for (int m = 0; m < M; m++) {
-                        const float2 *fi = (m == 0) ? xbuf : bbuf + (m - 1) * p.nint;
+                        const float2 *fi = (m == 0) ? X + xo : Y + (m - 1) * p.ylen;
                         const float2 lo = fi[stt + low], hi = fi[stt + high];
                         const float tr = __fadd_rn(__fmul_rn(omf, lo.x), __fmul_rn(fract, hi.x));
                         const float ti = __fadd_rn(__fmul_rn(omf, lo.y), __fmul_rn(fract, hi.y));
@@ -418,12 +491,12 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             /* samp_old for the next frame */
 #pragma unroll
             for (int q = 0; q < WB_NST; q++)
-                if (lane + 32 * q < nstash) xbuf[lane + 32 * q] = stash[q];
+                if (lane + 32 * q < nstash) X[lane + 32 * q] = stash[q];
             if (lane == 0) {
 #pragma unroll
                 for (int m = 0; m < M; m++) c.pb[m] = c.nb[m];              /* fsk->f_est = this frame's, :846 */
-                if (a.frame_log && frames - st->frames < (unsigned long long)a.log_cap) {
-                    float *l = a.frame_log + ((size_t)sg * a.log_cap + (size_t)(frames - st->frames)) * 8;
+                if (a.frame_log && frames < (unsigned)a.log_cap) {
+                    float *l = a.frame_log + ((size_t)sg * a.log_cap + frames) * 8;
                     l[0] = (float)nin;
                     for (int m = 0; m < 4; m++) l[1 + m] = m < M ? (float)c.nb[m] : 0.0f;
                     l[5] = c.norm; l[6] = c.ppm; l[7] = c.rx_timing;
@@ -445,8 +518,8 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             if (lane + 32 * q < nh) st->fft_est[lane + 32 * q] = est[q];
 #pragma unroll
         for (int q = 0; q < WB_NST; q++)
-            if (lane + 32 * q < nstash) st->samp_old[lane + 32 * q] = xbuf[lane + 32 * q];
-        unsigned long long rem = fill - pos;
+            if (lane + 32 * q < nstash) st->samp_old[lane + 32 * q] = X[lane + 32 * q];
+        const unsigned long long rem = fill - pos;
         const unsigned long long dstpos = (unsigned long long)a.headroom - rem;   /* remainder ends at the headroom mark */
         if (a.compact && rem > 0 && pos > dstpos) {
             /* less than one frame is left over: park it right before the headroom mark so that every
@@ -457,7 +530,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             const unsigned long long nbytes = rem * bps, sb = pos * bps, db = dstpos * bps;
             for (unsigned long long off = 0; off < nbytes; off += 32 * 8) {
                 unsigned char tmp[8];
-                unsigned long long o = off + (unsigned long long)lane * 8;
+                const unsigned long long o = off + (unsigned long long)lane * 8;
 #pragma unroll
                 for (int b = 0; b < 8; b++) tmp[b] = (o + b < nbytes) ? row[sb + o + b] : 0;
                 __syncwarp();
@@ -469,7 +542,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
         if (lane == 0) {
             for (int m = 0; m < M; m++) { st->phi_c[m] = c.phi_c[m]; st->fbin[m] = c.pb[m]; }
             st->norm_rx_timing = c.norm; st->ppm = c.ppm; st->rx_timing = c.rx_timing;
-            st->nin = nin; st->frames = frames;
+            st->nin = nin; st->frames += frames;
             if (a.compact) { st->in_pos = dstpos; st->in_fill = a.headroom; }
             else { st->in_pos = pos; st->in_fill = fill; }
             wb_cursor &cu = a.cursor[sg];

@@ -46,7 +46,8 @@ struct wb_fsk_params {
     int n_levels;             /* FFT schedule, leaf first */
     int lev_p[WB_MAX_LEVELS], lev_m[WB_MAX_LEVELS], lev_fstride[WB_MAX_LEVELS];
     int in_fmt, in_bps;       /* bytes per input sample */
-    int xlen, blen, sreg;     /* smem geometry: float2 per stream for x / the other tones, bytes per stream */
+    int xlen, ylen, blen, sreg; /* smem geometry per stream: float2 of X, of one other-tone buffer, of all of them
+                                  (>= Ndft: FFT work buffer); bytes per stream region (== 8 mod 16) */
     /* host-built constant tables (glibc cosf/sinf on the host = what the reference would use) */
     const float  *hann;       /* [Ndft]       reference src/fsk.c:94-111 */
     const float2 *tw;         /* [Ndft]       kiss_fft twiddles, reference src/kiss_fft.c:357-363 */

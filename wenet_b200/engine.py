@@ -166,10 +166,10 @@ class Engine:
         self.n_streams = n_streams
         self.keep_llr = keep_llr
         self.chunk_samples = chunk_samples
-        g = np.zeros(12, dtype=np.int32)
-        self._check(self.lib.wb_geometry(self.h, _ptr(g), 12))
+        g = np.zeros(14, dtype=np.int32)
+        self._check(self.lib.wb_geometry(self.h, _ptr(g), 14))
         (self.N, self.Nbits, self.Ts, self.P, self.Ndft, self.nmax, self.job_cap, self.sd_cap, self.Nsym, self.M,
-         self.max_iter, self.packet_syms) = [int(v) for v in g]
+         self.max_iter, self.packet_syms, self.streams_per_cta, self.fsk_smem_bytes) = [int(v) for v in g]
         self.Fs, self.Rs = Fs, Rs
 
     def _check(self, rc):
