@@ -171,11 +171,13 @@ static int build_fsk_params(const wb_config *cfg, wb_fsk_params *fp)
     for (int i = 1; i > 0 && i <= fp->N; i <<= 1) if (fp->N & i) Ndft = i;   /* reference src/fsk.c:169-173 */
     fp->Ndft = Ndft;
     fp->nstash = 4 * Ts;
+    fp->nst = 2 * Ts + Ts / 2;
     fp->step = Ts / P;
     fp->nint = (fp->Nsym + 1) * P;
     fp->nsteps = fp->Nmem - fp->step;
     fp->nmax = fp->N + Ts / 2;
-    if (Ndft > WB_MAX_NDFT || Ndft < 64) return wb_fail(WB_EINVAL, "Ndft = %d unsupported", Ndft);
+    if (Ndft > WB_MAX_NDFT || Ndft < 128) return wb_fail(WB_EINVAL, "Ndft = %d unsupported", Ndft);
+    if (fp->nint > WB_MAX_NINT) return wb_fail(WB_EINVAL, "too many integrator outputs per frame");
     if (fp->N - Ts / 2 < Ndft || fp->nmax >= 2 * Ndft || fp->nmax > WB_MAX_NIN)
         return wb_fail(WB_EINVAL, "frame length %d vs Ndft %d unsupported (needs exactly one estimator FFT per frame)", fp->N, Ndft);
     if (Fs / Ndft < 1) return wb_fail(WB_EINVAL, "Fs too low");
@@ -195,7 +197,7 @@ static int build_fsk_params(const wb_config *cfg, wb_fsk_params *fp)
     case WB_FMT_CU8: case WB_FMT_S16: fp->in_bps = 2; break;
     default: return wb_fail(WB_EINVAL, "unknown in_fmt %d", cfg->in_fmt);
     }
-    fp->xlen = (fp->nstash + fp->nmax + 1) & ~1;
+    fp->xlen = (fp->nst + fp->nmax + 1) & ~1;
     fp->ylen = (fp->nsteps + 1) & ~1;
     fp->blen = std::max((M - 1) * fp->ylen, Ndft);
     int bytes = (fp->xlen + fp->blen) * 8 + ((fp->nint * 4 + 7) & ~7);
@@ -235,6 +237,7 @@ static int upload_tables(wb_engine *e)
     int nl = fft_factor(Ndft, fac);
     if (nl > WB_MAX_LEVELS) return wb_fail(WB_EINVAL, "FFT too deep");
     for (int l = 0; l < nl; l++) if (fac[2 * l] != 4 && fac[2 * l] != 2) return wb_fail(WB_EINVAL, "unsupported FFT radix");
+    for (int l = 0; l < nl - 1; l++) if (fac[2 * l] != 4) return wb_fail(WB_EINVAL, "unsupported FFT factorisation");
     fft_perm(perm, 0, 0, 1, fac);
     fp.n_levels = nl;
     {
@@ -242,6 +245,8 @@ static int upload_tables(wb_engine *e)
         for (int l = 0; l < nl; l++) {             /* top level first in fac[], leaf first in lev_* */
             int dst = nl - 1 - l;
             fp.lev_p[dst] = fac[2 * l]; fp.lev_m[dst] = fac[2 * l + 1]; fp.lev_fstride[dst] = fstride;
+            int sh = 0; while ((1 << sh) < fac[2 * l + 1]) sh++;
+            fp.lev_sh[dst] = sh;
             fstride *= fac[2 * l];
         }
     }
@@ -249,7 +254,7 @@ static int upload_tables(wb_engine *e)
     {
         hcpx d = hcexpj((float)(2 * M_PI * ((float)fp.Rs / (float)(fp.P * fp.Rs))));
         hcpx ph; ph.r = 1; ph.i = 0;
-        for (int i = 0; i < fp.nint; i++) { pft[i] = ph; ph = hcmul(ph, d); }
+        for (int i = 0; i < fp.nint; i++) { pft[i] = ph; fp.pftc[i] = make_float2(ph.r, ph.i); ph = hcmul(ph, d); }
     }
     /* per-bin tone oscillators, reference src/fsk.c:756-764, :671 */
     for (int b = 0; b < nh; b++) {
@@ -451,7 +456,8 @@ extern "C" int wb_create(const wb_config *cfg, wb_engine **out)
         int dev_smem_sm = 0, dev_smem_blk = 0;
         CRE(cudaDeviceGetAttribute(&dev_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cfg->device));
         CRE(cudaDeviceGetAttribute(&dev_smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
-        auto smem_for = [&](int spb) { return ((sizeof(wb_fsk_sc) * spb + 127) / 128) * 128 + (size_t)spb * e->fp.sreg; };
+        auto smem_for = [&](int spb) { return ((sizeof(wb_fsk_sc) * spb + 127) / 128) * 128 + (size_t)3 * (e->fp.Ndft / 4) * sizeof(float2) +
+                                              (size_t)spb * e->fp.sreg; };
         int spb = 0;
         for (int ctas = 2; ctas >= 1 && spb == 0; ctas--)
             for (int t = max_spb; t >= (ctas == 2 ? 4 : 1); t--)

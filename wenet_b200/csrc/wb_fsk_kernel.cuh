@@ -19,10 +19,10 @@
  *   CTA = spb streams (runtime; 14 for 2-FSK at Ts = 8 so that two CTAs = 28 streams fit one SM and
  *   4096 streams are all resident on 148 SMs), one "stream warp" per stream, frames in lock step.
  *
- *   A  (stream warps)  land the prefetched frame in shared memory, window + 256-point FFT in the
- *                      reference's butterfly order, spectrum IIR (registers), warp-argmax peak
- *                      picking, then issue the global loads of the NEXT frame into registers
- *                      (consumed a whole frame later: HBM latency is off the critical path).
+ *   A  (stream warps)  bring the frame into shared memory (L2 hits: each frame is prefetched into
+ *                      L2 one frame ahead, so HBM latency is off the critical path and no registers
+ *                      are tied up), window + 256-point FFT in the reference's butterfly order,
+ *                      spectrum IIR (registers), warp-argmax peak picking.
  *   B1 (warp 0, lane = (tone, stream))  ONLY the sequential part of the mixer: oscillator
  *                      recurrence + down-mix product, written in place over the samples.
  *   B2 (stream warps, lanes = integrator outputs)  Ts-tap sums in the reference's ring-buffer slot
@@ -35,10 +35,13 @@
  * The sequential phases cost one warp's issue slots for ALL streams of the CTA (every lane carries
  * a different dependent chain); while one CTA of an SM is in B1/B3 the other one runs A/B2/C.
  *
- * Shared memory per stream: X[nstash + nmax] float2 (old + new samples -> tone 0 mixer products ->
- * tone 0 integrator outputs, all in place), Y[(M-1) * ylen] float2 for the other tones (the FFT work
- * buffer in phase A) and E[nint] floats.  Stream regions are an odd multiple of 8 bytes mod 128
- * apart so the lanes of warp 0 (one stream each) hit distinct banks.
+ * Shared memory per stream: X[nst + nmax] float2 (the nst = 2Ts + Ts/2 old samples the mixer can reach
+ * back to + the new ones -> tone 0 mixer products -> tone 0 integrator outputs, all in place),
+ * Y[(M-1) * ylen] float2 for the other tones (the FFT work buffer in phase A) and E[nint] floats.
+ * Stream regions are an odd multiple of 8 bytes mod 128 apart so the lanes of warp 0 (one stream
+ * each) hit distinct banks.  For Ts = 8 the mixer products / integrator outputs are stored with
+ * their low three index bits XORed with bits 4..6 (wb_phys) so that B2's lanes, which walk blocks
+ * of eight, spread over all banks.  Per CTA: the frame scalars and the FFT twiddles (1.5 KB).
  * HBM traffic: every input sample is read once (8 B as cf32), 4 B x Nbits/N written.
  */
 #ifndef WB_FSK_KERNEL_CUH
@@ -47,7 +50,7 @@
 #include "wb_internal.h"
 #include "wb_math.h"
 
-#define WB_NST ((WB_MAX_NSTASH + 31) / 32)
+#define WB_NST 1                     /* stash registers per lane: 2*Ts + Ts/2 <= 25 samples are carried over */
 #define WB_NEQ (WB_MAX_NDFT / 2 / 32)
 
 struct wb_fsk_sc {                 /* per-stream frame scalars in shared memory (88 bytes) */
@@ -104,71 +107,83 @@ __device__ __forceinline__ float2 wb_convert(int fmt, unsigned lo, unsigned hi)
     return v;
 }
 
+/* input samples are touched exactly once: keep them out of L1 so the small constant tables stay resident */
 template <bool CF32>
 __device__ __forceinline__ void wb_load_raw(int fmt, const unsigned char *p, unsigned long long idx, unsigned &lo, unsigned &hi)
 {
     if (CF32) {
-        uint2 r = __ldg(reinterpret_cast<const uint2 *>(p) + idx);
-        lo = r.x; hi = r.y;
+        asm("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(reinterpret_cast<const uint2 *>(p) + idx));
     } else if (fmt == WB_FMT_CS16) {
-        lo = __ldg(reinterpret_cast<const unsigned *>(p) + idx); hi = 0u;
+        asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(lo) : "l"(reinterpret_cast<const unsigned *>(p) + idx));
+        hi = 0u;
     } else {
-        lo = __ldg(reinterpret_cast<const unsigned short *>(p) + idx); hi = 0u;
+        unsigned short t;
+        asm("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(t) : "l"(reinterpret_cast<const unsigned short *>(p) + idx));
+        lo = t; hi = 0u;
     }
 }
 
-/* one mixer step: product with the conjugated oscillator (reference src/fsk.c:794-798) */
-#define WB_MIX_STEP(SRC, DST, N)                                                            \
-    do {                                                                                    \
-        const float2 x_ = (SRC)[N];                                                         \
-        float2 o_;                                                                          \
-        o_.x = __fadd_rn(__fmul_rn(x_.x, ph.x), __fmul_rn(x_.y, ph.y));                     \
-        o_.y = __fsub_rn(__fmul_rn(x_.y, ph.x), __fmul_rn(x_.x, ph.y));                     \
-        (DST)[N] = o_;                                                                      \
-        ph = wb_cmul2(ph, d);                                                               \
-    } while (0)
+/* product with a unit twiddle tw[0] = (cosf(-0.0), sinf(-0.0)) = (1, -0): the two multiplications by 1 are
+   exact for every input and dropped; the two by -0 are kept so NaN/Inf samples propagate as in kiss_fft */
+__device__ __forceinline__ float2 wb_ucmul(float2 a)
+{
+    float2 c;
+    c.x = __fsub_rn(a.x, __fmul_rn(a.y, -0.0f));
+    c.y = __fadd_rn(__fmul_rn(a.x, -0.0f), a.y);
+    return c;
+}
+
+template <bool SWZ>
+__device__ __forceinline__ int wb_phys(int n)
+{
+    /* bank swizzle of the product / integrator arrays: a permutation inside each aligned block of 8.
+       Block 48 and the partial block 49 (Nsym = 48) have key 0, so nothing is mapped past the end. */
+    return SWZ ? ((n & ~7) | ((n ^ (n >> 4)) & 7)) : n;
+}
 
 template <int M, int TS, bool CF32>
 __global__ void __launch_bounds__(M == 2 ? 448 : 256, 2)
 wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 {
     constexpr int NPRE = (TS * WB_FRAME_SYMS + TS / 2 + 31) / 32;     /* lanes x NPRE >= nmax */
+    constexpr bool SWZ = (TS == 8);
+    constexpr int NBLK = WB_FRAME_SYMS + 1;                           /* integrator outputs come in 49 blocks of P */
     extern __shared__ __align__(16) unsigned char wb_fsk_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int spb = a.spb;
     const int sg = blockIdx.x * spb + warp;
     const bool have = sg < a.n_streams;
+    const int Ndft = p.Ndft, nh = Ndft >> 1, nst = p.nst, fmt = p.in_fmt;
 
     wb_fsk_sc *sc = reinterpret_cast<wb_fsk_sc *>(wb_fsk_raw);
-    unsigned char *regions = wb_fsk_raw + ((sizeof(wb_fsk_sc) * spb + 127) / 128) * 128;
+    float2 *TW = reinterpret_cast<float2 *>(wb_fsk_raw + ((sizeof(wb_fsk_sc) * spb + 127) / 128) * 128);
+    unsigned char *regions = reinterpret_cast<unsigned char *>(TW + 3 * (Ndft >> 2));
     float2 *X = reinterpret_cast<float2 *>(regions + (size_t)warp * p.sreg);
     float2 *Y = X + p.xlen;
     float *E = reinterpret_cast<float *>(Y + p.blen);
-    const int Ndft = p.Ndft, nh = Ndft >> 1, nstash = p.nstash, fmt = p.in_fmt;
 
     /* ---- per-stream state -> registers / shared memory ---- */
     wb_stream_state *st = have ? a.state + sg : nullptr;
-    const unsigned char *in = a.in + (size_t)(have ? sg : 0) * a.in_stride;
-    float *sdrow = a.sd + (size_t)(have ? sg : 0) * a.sd_stride + WB_CARRY_CAP;
-    unsigned long long pos = 0, fill = 0, pos0 = 0;
+    /* row positions in samples fit 32 bits (wb_create checks); the row pointers are recomputed from the stream
+       index where they are needed instead of being carried through the frame loop (register pressure) */
+#define WB_ROW_IN(SG) (a.in + (size_t)(SG) * a.in_stride)
+#define WB_ROW_SD(SG) (a.sd + (size_t)(SG) * a.sd_stride + WB_CARRY_CAP)
+    const int sgc = have ? sg : 0;
+    unsigned pos = 0, fill = 0, pos0 = 0;
     unsigned frames = 0;
     int nin = p.N;
     unsigned n_out = 0;
     float est[WB_NEQ];
-    float2 stash[WB_NST];
-    unsigned pre_lo[NPRE], pre_hi[NPRE];
+    float2 stash = make_float2(0.0f, 0.0f);
 #pragma unroll
     for (int q = 0; q < WB_NEQ; q++) est[q] = 0.0f;
-#pragma unroll
-    for (int q = 0; q < WB_NST; q++) stash[q] = make_float2(0.0f, 0.0f);
+    for (int i = tid; i < 3 * (Ndft >> 2); i += blockDim.x) TW[i] = __ldg(&p.tw[i]);
     if (have) {
-        pos = pos0 = st->in_pos; fill = st->in_fill; nin = st->nin;
+        pos = pos0 = (unsigned)st->in_pos; fill = (unsigned)st->in_fill; nin = st->nin;
 #pragma unroll
         for (int q = 0; q < WB_NEQ; q++)
             if (lane + 32 * q < nh) est[q] = st->fft_est[lane + 32 * q];
-#pragma unroll
-        for (int q = 0; q < WB_NST; q++)
-            if (lane + 32 * q < nstash) X[lane + 32 * q] = st->samp_old[lane + 32 * q];
+        if (lane < nst) X[lane] = st->samp_old[lane];
         if (lane == 0) {
             wb_fsk_sc &c = sc[warp];
             for (int m = 0; m < M; m++) { c.phi_c[m] = st->phi_c[m]; c.pb[m] = (short)st->fbin[m]; c.nb[m] = 0; }
@@ -181,86 +196,151 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
         c.nin = p.N; c.flags = 0; c.nin_next = p.N; c.norm = 0.0f; c.ppm = 0.0f; c.rx_timing = 0.0f;
         c.low = c.high = 0; c.fract = 0.0f;
     }
-    /* prefetch the first frame */
-#pragma unroll
-    for (int q = 0; q < NPRE; q++) {
-        const int n = lane + 32 * q;
-        pre_lo[q] = pre_hi[q] = 0u;
-        if (have && n < p.nmax && pos + n < fill) wb_load_raw<CF32>(fmt, in, pos + n, pre_lo[q], pre_hi[q]);
-    }
-
     const float omt = __fsub_rn(1.0f, p.tc);
+    const bool blocked = (p.step == 1);          /* P == Ts: the configuration every Wenet script uses */
 
     for (;;) {
-        const bool active = have && (pos + (unsigned long long)nin <= fill) && (n_out + (unsigned)p.Nbits <= a.sd_cap);
+        const bool active = have && (pos + (unsigned)nin <= fill) && (n_out + (unsigned)p.Nbits <= a.sd_cap);
         if (!__syncthreads_or(active)) break;
-        const unsigned long long pos_next = pos + nin;
-        const int xo = nstash - (p.Nmem - nin);      /* X index of the first mixer sample */
+        const unsigned pos_next = pos + nin;
+        const int xo = nst - (p.Nmem - nin);         /* X index of the first mixer sample */
 
         /* ================= A: stream warps ================= */
         if (active) {
-#pragma unroll
-            for (int q = 0; q < NPRE; q++) {
-                const int n = lane + 32 * q;
-                if (n < p.nmax) X[nstash + n] = wb_convert<CF32>(fmt, pre_lo[q], pre_hi[q]);
-            }
-            __syncwarp();
-            /* window the first nin - Ndft samples, zero-pad, in the leaf order of the DIT recursion
-               (reference src/fsk.c:583-603, src/kiss_fft.c:238-306) */
+            /* the leaf butterflies' table entries first: their latency hides behind the landing of the frame */
+            const int pp0 = p.lev_p[0], istr = Ndft / pp0;
             const int nwin = min(nin - Ndft, Ndft);
-            float2 *F = Y;
-            for (int o = lane; o < Ndft; o += 32) {
-                const int idx = __ldg(&p.perm[o]);
-                float2 v = make_float2(0.0f, 0.0f);
-                if (idx < nwin) {
-                    const float h = __ldg(&p.hann[idx]);
-                    const float2 x = X[nstash + idx];
-                    v.x = __fmul_rn(h, x.x); v.y = __fmul_rn(h, x.y);
+            int lbase[2];
+            float lh[2][4];
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                const int t = lane + 32 * b;
+                lbase[b] = (t < istr) ? (int)__ldg(&p.perm[t * pp0]) : 0;
+            }
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+#pragma unroll
+                for (int dd = 0; dd < 4; dd++) {
+                    const int n = lbase[b] + dd * istr;
+                    lh[b][dd] = (lane + 32 * b < istr && dd < pp0 && n < nwin) ? __ldg(&p.hann[n]) : 0.0f;
                 }
-                F[o] = v;
+            }
+            {
+                /* this frame's samples: L2 hits (prefetched into L2 a frame ago, see below), straight to shared
+                   memory.  The registers are only held for the round trip, at a point of low register pressure. */
+                int sgv = sgc;
+                asm volatile("" : "+r"(sgv));        /* opaque: recompute the row pointer here, do not carry it */
+                const unsigned char *in = WB_ROW_IN(sgv);
+                unsigned pre_lo[NPRE], pre_hi[NPRE];
+#pragma unroll
+                for (int q = 0; q < NPRE; q++) {
+                    const int n = lane + 32 * q;
+                    pre_lo[q] = pre_hi[q] = 0u;
+                    if (n < p.nmax && pos + n < fill) wb_load_raw<CF32>(fmt, in, pos + n, pre_lo[q], pre_hi[q]);
+                }
+                /* next frame -> L2: one 128-byte line per lane, no registers held */
+                {
+                    const unsigned long long b0 = (unsigned long long)pos_next * p.in_bps;
+                    const unsigned long long off = (b0 & ~127ULL) + 128ULL * lane;
+                    if (off < b0 + (unsigned long long)p.nmax * p.in_bps && off < (unsigned long long)fill * p.in_bps)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(in + off));
+                }
+#pragma unroll
+                for (int q = 0; q < NPRE; q++) {
+                    const int n = lane + 32 * q;
+                    if (n < p.nmax) X[nst + n] = wb_convert<CF32>(fmt, pre_lo[q], pre_hi[q]);
+                }
             }
             __syncwarp();
-            for (int L = 0; L < p.n_levels; L++) {
-                const int pp = p.lev_p[L], mm = p.lev_m[L], fs = p.lev_fstride[L];
-                const int nbf = Ndft / pp;
-                for (int t = lane; t < nbf; t += 32) {
-                    const int blk = t / mm, k = t - blk * mm;
-                    const int base = blk * pp * mm + k;
-                    if (pp == 4) {      /* reference src/kiss_fft.c:44-90, forward */
-                        const float2 f0 = F[base], f1 = F[base + mm], f2 = F[base + 2 * mm], f3 = F[base + 3 * mm];
-                        const float2 s0 = wb_cmul2(f1, __ldg(&p.tw[k * fs]));
-                        const float2 s1 = wb_cmul2(f2, __ldg(&p.tw[2 * k * fs]));
-                        const float2 s2 = wb_cmul2(f3, __ldg(&p.tw[3 * k * fs]));
-                        const float2 s5 = make_float2(__fsub_rn(f0.x, s1.x), __fsub_rn(f0.y, s1.y));
-                        const float2 aa = make_float2(__fadd_rn(f0.x, s1.x), __fadd_rn(f0.y, s1.y));
+            /* Estimator FFT (reference src/fsk.c:583-628, src/kiss_fft.c:238-306): decimation in time, the
+               reference's butterfly order.  Leaf level fused with the window: leaf butterfly t combines the
+               inputs perm[t*p] + d*Ndft/p, of which only those below nwin = nin - Ndft are non-zero. */
+            float2 *F = Y;
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                const int t = lane + 32 * b;
+                if (t < istr) {
+                    float2 f[4];
+#pragma unroll
+                    for (int dd = 0; dd < 4; dd++) {
+                        const int n = lbase[b] + dd * istr;
+                        f[dd] = make_float2(0.0f, 0.0f);
+                        if (dd < pp0 && n < nwin) {
+                            const float2 x = X[nst + n];
+                            f[dd].x = __fmul_rn(lh[b][dd], x.x); f[dd].y = __fmul_rn(lh[b][dd], x.y);
+                        }
+                    }
+                    if (pp0 == 4) {     /* reference src/kiss_fft.c:44-90 with m = 1: all twiddles are tw[0] */
+                        const float2 s0 = wb_ucmul(f[1]), s1 = wb_ucmul(f[2]), s2 = wb_ucmul(f[3]);
+                        const float2 s5 = make_float2(__fsub_rn(f[0].x, s1.x), __fsub_rn(f[0].y, s1.y));
+                        const float2 aa = make_float2(__fadd_rn(f[0].x, s1.x), __fadd_rn(f[0].y, s1.y));
                         const float2 s3 = make_float2(__fadd_rn(s0.x, s2.x), __fadd_rn(s0.y, s2.y));
                         const float2 s4 = make_float2(__fsub_rn(s0.x, s2.x), __fsub_rn(s0.y, s2.y));
-                        F[base + 2 * mm] = make_float2(__fsub_rn(aa.x, s3.x), __fsub_rn(aa.y, s3.y));
-                        F[base] = make_float2(__fadd_rn(aa.x, s3.x), __fadd_rn(aa.y, s3.y));
-                        F[base + mm] = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));
-                        F[base + 3 * mm] = make_float2(__fsub_rn(s5.x, s4.y), __fadd_rn(s5.y, s4.x));
-                    } else {            /* reference src/kiss_fft.c:22-42 */
-                        const float2 f0 = F[base], f1 = F[base + mm];
-                        const float2 tt = wb_cmul2(f1, __ldg(&p.tw[k * fs]));
-                        F[base + mm] = make_float2(__fsub_rn(f0.x, tt.x), __fsub_rn(f0.y, tt.y));
-                        F[base] = make_float2(__fadd_rn(f0.x, tt.x), __fadd_rn(f0.y, tt.y));
+                        /* (stream regions are only 8-byte aligned: float2 stores) */
+                        F[4 * t] = make_float2(__fadd_rn(aa.x, s3.x), __fadd_rn(aa.y, s3.y));
+                        F[4 * t + 1] = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));
+                        F[4 * t + 2] = make_float2(__fsub_rn(aa.x, s3.x), __fsub_rn(aa.y, s3.y));
+                        F[4 * t + 3] = make_float2(__fsub_rn(s5.x, s4.y), __fadd_rn(s5.y, s4.x));
+                    } else {            /* reference src/kiss_fft.c:22-42 with m = 1 */
+                        const float2 tt = wb_ucmul(f[1]);
+                        F[2 * t] = make_float2(__fadd_rn(f[0].x, tt.x), __fadd_rn(f[0].y, tt.y));
+                        F[2 * t + 1] = make_float2(__fsub_rn(f[0].x, tt.x), __fsub_rn(f[0].y, tt.y));
                     }
+                }
+            }
+            __syncwarp();
+            for (int L = 1; L < p.n_levels - 1; L++) {      /* middle levels: radix 4, twiddles from shared memory */
+                const int sh = p.lev_sh[L], mm = 1 << sh, fs = p.lev_fstride[L];
+                for (int t = lane; t < (Ndft >> 2); t += 32) {
+                    const int k = t & (mm - 1);
+                    const int base = ((t >> sh) << (sh + 2)) + k;
+                    const float2 f0 = F[base], f1 = F[base + mm], f2 = F[base + 2 * mm], f3 = F[base + 3 * mm];
+                    const float2 s0 = wb_cmul2(f1, TW[k * fs]);
+                    const float2 s1 = wb_cmul2(f2, TW[2 * k * fs]);
+                    const float2 s2 = wb_cmul2(f3, TW[3 * k * fs]);
+                    const float2 s5 = make_float2(__fsub_rn(f0.x, s1.x), __fsub_rn(f0.y, s1.y));
+                    const float2 aa = make_float2(__fadd_rn(f0.x, s1.x), __fadd_rn(f0.y, s1.y));
+                    const float2 s3 = make_float2(__fadd_rn(s0.x, s2.x), __fadd_rn(s0.y, s2.y));
+                    const float2 s4 = make_float2(__fsub_rn(s0.x, s2.x), __fsub_rn(s0.y, s2.y));
+                    F[base + 2 * mm] = make_float2(__fsub_rn(aa.x, s3.x), __fsub_rn(aa.y, s3.y));
+                    F[base] = make_float2(__fadd_rn(aa.x, s3.x), __fadd_rn(aa.y, s3.y));
+                    F[base + mm] = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));
+                    F[base + 3 * mm] = make_float2(__fsub_rn(s5.x, s4.y), __fadd_rn(s5.y, s4.x));
                 }
                 __syncwarp();
             }
-            /* magnitude spectrum, band limits, IIR (reference src/fsk.c:610-628) */
+            /* top level (radix 4, m = Ndft/4, fstride 1) fused with the magnitude spectrum, band limits and
+               IIR (reference src/fsk.c:610-628): butterfly k yields bins k and k + m, the only ones below
+               Ndft/2; lane + 32 q is exactly the layout of est[] */
             float v[WB_NEQ];
 #pragma unroll
-            for (int q = 0; q < WB_NEQ; q++) {
-                const int i = lane + 32 * q;
-                v[q] = 0.0f;
-                if (i < nh) {
-                    const float2 Xf = F[i];
-                    float pw = __fadd_rn(__fmul_rn(Xf.x, Xf.x), __fmul_rn(Xf.y, Xf.y));
-                    if (i < p.f_min || i >= p.f_max - 1) pw = 0.0f;
-                    est[q] = __fadd_rn(__fmul_rn(est[q], omt), __fmul_rn(__fsqrt_rn(pw), p.tc));
-                    v[q] = est[q];
-                }
+            for (int q = 0; q < WB_NEQ; q++) v[q] = 0.0f;
+            {
+                const int mtop = Ndft >> 2;
+#define WB_TOP_BFLY(K, Q0, Q1)                                                                        \
+                do {                                                                                  \
+                    const int k_ = (K);                                                               \
+                    const float2 f0 = F[k_], f1 = F[k_ + mtop], f2 = F[k_ + 2 * mtop], f3 = F[k_ + 3 * mtop]; \
+                    const float2 s0 = wb_cmul2(f1, TW[k_]);                                           \
+                    const float2 s1 = wb_cmul2(f2, TW[2 * k_]);                                       \
+                    const float2 s2 = wb_cmul2(f3, TW[3 * k_]);                                       \
+                    const float2 s5 = make_float2(__fsub_rn(f0.x, s1.x), __fsub_rn(f0.y, s1.y));     \
+                    const float2 aa = make_float2(__fadd_rn(f0.x, s1.x), __fadd_rn(f0.y, s1.y));     \
+                    const float2 s3 = make_float2(__fadd_rn(s0.x, s2.x), __fadd_rn(s0.y, s2.y));     \
+                    const float2 s4 = make_float2(__fsub_rn(s0.x, s2.x), __fsub_rn(s0.y, s2.y));     \
+                    const float2 o0 = make_float2(__fadd_rn(aa.x, s3.x), __fadd_rn(aa.y, s3.y));     \
+                    const float2 o1 = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));     \
+                    float pw0 = __fadd_rn(__fmul_rn(o0.x, o0.x), __fmul_rn(o0.y, o0.y));              \
+                    float pw1 = __fadd_rn(__fmul_rn(o1.x, o1.x), __fmul_rn(o1.y, o1.y));              \
+                    if (k_ < p.f_min || k_ >= p.f_max - 1) pw0 = 0.0f;                                \
+                    if (k_ + mtop < p.f_min || k_ + mtop >= p.f_max - 1) pw1 = 0.0f;                  \
+                    est[Q0] = __fadd_rn(__fmul_rn(est[Q0], omt), __fmul_rn(__fsqrt_rn(pw0), p.tc));   \
+                    est[Q1] = __fadd_rn(__fmul_rn(est[Q1], omt), __fmul_rn(__fsqrt_rn(pw1), p.tc));   \
+                    v[Q0] = est[Q0]; v[Q1] = est[Q1];                                                 \
+                } while (0)
+                if (mtop == 64) { WB_TOP_BFLY(lane, 0, 2); WB_TOP_BFLY(lane + 32, 1, 3); }
+                else { WB_TOP_BFLY(lane, 0, 1); }
+#undef WB_TOP_BFLY
             }
             /* M maxima with +-f_zero blanking (reference src/fsk.c:635-654), then ascending order */
             int freqi[M];
@@ -290,24 +370,15 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 for (int j = i; j > 0; j--)
                     if (freqi[j - 1] > freqi[j]) { const int t = freqi[j]; freqi[j] = freqi[j - 1]; freqi[j - 1] = t; }
             }
-            /* the samples to stash for the next frame (reference src/fsk.c:851) sit where the mixer
-               products are about to land: lift them into registers */
-#pragma unroll
-            for (int q = 0; q < WB_NST; q++)
-                if (lane + 32 * q < nstash) stash[q] = X[nin + lane + 32 * q];
+            /* the samples the next frame's mixer reaches back to (reference src/fsk.c:851 keeps 4 Ts, uses at most
+               2 Ts + Ts/2) sit where the mixer products are about to land: lift them into registers */
+            if (lane < nst) stash = X[nin + lane];
             if (lane == 0) {
                 wb_fsk_sc &c = sc[warp];
                 const bool first = c.pb[0] == 0;         /* fsk->f_est[0] < 1, reference src/fsk.c:729 */
 #pragma unroll
                 for (int m = 0; m < M; m++) { c.nb[m] = (short)freqi[m]; if (first) c.pb[m] = (short)freqi[m]; }
                 c.nin = nin; c.flags = 1;
-            }
-            /* next frame: global loads now, consumed at the top of the next iteration */
-#pragma unroll
-            for (int q = 0; q < NPRE; q++) {
-                const int n = lane + 32 * q;
-                pre_lo[q] = pre_hi[q] = 0u;
-                if (n < p.nmax && pos_next + n < fill) wb_load_raw<CF32>(fmt, in, pos_next + n, pre_lo[q], pre_hi[q]);
             }
         } else if (lane == 0) {
             sc[warp].flags = 0;
@@ -327,62 +398,143 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 ph = wb_cmul2(__ldg(&p.back[nin_idx * nh + pb]), ph);     /* reference src/fsk.c:756-759 */
                 float2 d = __ldg(&p.dphi[pb]);
                 const float2 dnew = __ldg(&p.dphi[nbn]);
-                const float2 *src = Xs + (nstash - nold);
-                float2 *dst = (m == 0) ? Xs + (nstash - nold) : Xs + p.xlen + (m - 1) * p.ylen;
+                const float2 *src = Xs + (nst - nold);
+                float2 *dst = (m == 0) ? Xs + (nst - nold) : Xs + p.xlen + (m - 1) * p.ylen;
                 const int nsteps = p.nsteps;
-                const int nslow = 2 * p.Ts + p.Ts / 2 + 1;                /* > every possible nold */
-                int n = 0;
+                const int nold_lo = 2 * p.Ts - p.Ts / 2, nold_hi = 2 * p.Ts + p.Ts / 2;
+                /* batches of eight steps: all eight samples are loaded before the (in-place, swizzled) stores.
+                   cmult(sample, cconj(phi)) then phi *= dphi: reference src/fsk.c:794-798. */
+#define WB_B1_STEP(J)                                                                                   \
+                do {                                                                                    \
+                    const float ox_ = __fadd_rn(__fmul_rn(xv[J].x, ph.x), __fmul_rn(xv[J].y, ph.y));    \
+                    const float oy_ = __fsub_rn(__fmul_rn(xv[J].y, ph.x), __fmul_rn(xv[J].x, ph.y));    \
+                    xv[J] = make_float2(ox_, oy_);                                                      \
+                    ph = wb_cmul2(ph, d);                                                               \
+                } while (0)
+                int n0 = 0;
+                /* (a) the batches that can contain the old -> new sample switch */
 #pragma unroll 1
-                for (; n < nslow; n++) {
-                    if (n == nold) {        /* old -> new samples: comp_normalize + new tone, src/fsk.c:787-788 */
-                        const float av = __fsqrt_rn(__fadd_rn(__fmul_rn(ph.x, ph.x), __fmul_rn(ph.y, ph.y)));
-                        ph.x = __fdiv_rn(ph.x, av); ph.y = __fdiv_rn(ph.y, av);
-                        d = dnew;
-                    }
-                    WB_MIX_STEP(src, dst, n);
-                }
-#pragma unroll 1
-                for (; n + 8 <= nsteps; n += 8) {
+                for (; n0 <= nold_hi; n0 += 8) {
+                    const int kb = SWZ ? ((n0 >> 4) & 7) : 0;
+                    float2 xv[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) WB_MIX_STEP(src + n, dst + n, j);
+                    for (int j = 0; j < 8; j++) xv[j] = src[n0 + j];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        if (n0 + j == nold) {   /* comp_normalize + this frame's tone, reference src/fsk.c:787-788 */
+                            const float av = __fsqrt_rn(__fadd_rn(__fmul_rn(ph.x, ph.x), __fmul_rn(ph.y, ph.y)));
+                            ph.x = __fdiv_rn(ph.x, av); ph.y = __fdiv_rn(ph.y, av);
+                            d = dnew;
+                        }
+                        WB_B1_STEP(j);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; j++) dst[n0 + (j ^ kb)] = xv[j];
                 }
+                /* (b) full batches, branch-free */
 #pragma unroll 1
-                for (; n < nsteps; n++) WB_MIX_STEP(src, dst, n);
+                for (; n0 + 8 <= nsteps; n0 += 8) {
+                    const int kb = SWZ ? ((n0 >> 4) & 7) : 0;
+                    float2 xv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) xv[j] = src[n0 + j];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) WB_B1_STEP(j);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) dst[n0 + (j ^ kb)] = xv[j];
+                }
+                /* (c) the last, partial batch (its swizzle key is 0) */
+                {
+                    const int kb = SWZ ? ((n0 >> 4) & 7) : 0;
+#pragma unroll 1
+                    for (int j = 0; n0 + j < nsteps; j++) {
+                        float2 xv[1];
+                        xv[0] = src[n0 + j];
+                        WB_B1_STEP(0);
+                        dst[n0 + (j ^ kb)] = xv[0];
+                    }
+                }
+#undef WB_B1_STEP
                 c.phi_c[m] = ph;
             }
         }
         __syncthreads();
 
-        /* ================= B2: stream warps, lanes = integrator outputs ================= */
-        if (active) {
-            /* f_int[m][i] = sum of the Ts ring-buffer slots after mixer step i*step + Ts - 1, added in slot
-               order (reference src/fsk.c:835-838): slot j holds the product of the step n in
-               [i*step, i*step + Ts) with n mod Ts == j.  In place: output i overwrites product i. */
+        /* ================= B2: stream warps: Ts-tap integrator sums, |.|^2 over tones ================= */
+        /* f_int[m][i] = sum of the Ts ring-buffer slots after mixer step i*step + Ts - 1, added in slot order
+           (reference src/fsk.c:835-838): slot j holds the product of the step n in [i*step, i*step + Ts) with
+           n mod Ts == j.  In place: output i overwrites product i. */
+        if (active && blocked) {
+            /* step = 1: lane u owns outputs Ts*u .. Ts*u + Ts - 1.  It needs products Ts*u .. Ts*u + 2Ts - 2; output
+               Ts*u + t adds, in slot order, the first t products of block u+1 (a running prefix shared by all t)
+               and then products t .. Ts-1 of block u.  e goes to E[t * 49 + u] (conflict-free here, and B3 knows
+               the positions at compile time). */
+            for (int u0 = 0; u0 < NBLK; u0 += 32) {
+                const int u = u0 + lane;
+                const bool valid = u < NBLK;
+#pragma unroll
+                for (int m = 0; m < M; m++) {
+                    float2 *P = (m == 0) ? X + xo : Y + (m - 1) * p.ylen;
+                    float2 vv[2 * TS - 1];
+                    if (valid) {
+                        const int k0 = SWZ ? ((u >> 1) & 7) : 0, k1 = SWZ ? (((u + 1) >> 1) & 7) : 0;
+#pragma unroll
+                        for (int o = 0; o < TS; o++) vv[o] = P[TS * u + (o ^ k0)];
+#pragma unroll
+                        for (int o = 0; o < TS - 1; o++) vv[TS + o] = P[TS * (u + 1) + (o ^ k1)];
+                    }
+                    __syncwarp();
+                    if (valid) {
+                        const int k0 = SWZ ? ((u >> 1) & 7) : 0;
+                        float qr = 0.0f, qi = 0.0f;
+#pragma unroll
+                        for (int t = 0; t < TS; t++) {
+                            float sr, si;
+                            int o0;
+                            if (t == 0) { sr = vv[0].x; si = vv[0].y; o0 = 1; }
+                            else {
+                                if (t == 1) { qr = vv[TS].x; qi = vv[TS].y; }
+                                else { qr = __fadd_rn(qr, vv[TS + t - 1].x); qi = __fadd_rn(qi, vv[TS + t - 1].y); }
+                                sr = qr; si = qi; o0 = t;
+                            }
+#pragma unroll
+                            for (int o = 0; o < TS; o++)
+                                if (o >= o0) { sr = __fadd_rn(sr, vv[o].x); si = __fadd_rn(si, vv[o].y); }
+                            P[TS * u + (t ^ k0)] = make_float2(sr, si);
+                            const float pw = __fadd_rn(__fmul_rn(sr, sr), __fmul_rn(si, si));
+                            float *ep = E + t * NBLK + u;
+                            if (m == 0) *ep = pw;
+                            else *ep = __fadd_rn(*ep, pw);               /* reference src/fsk.c:864-867 */
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        } else if (active) {
+            /* general P: lanes = outputs, ring slots by modular arithmetic, E linear */
             const int step = p.step;
-            int r = (lane * step) % TS;                  /* (i * step) mod Ts for this lane's output */
-            const int rinc = (32 * step) % TS;
             for (int i0 = 0; i0 < p.nint; i0 += 32) {
                 const int i = i0 + lane;
                 const bool valid = i < p.nint;
                 float2 f[M];
                 float e = 0.0f;
                 if (valid) {
-                    const int n0 = i * step;
+                    const int n0 = i * step, r = n0 % TS;
 #pragma unroll
                     for (int m = 0; m < M; m++) {
-                        const float2 *P = (m == 0) ? X + xo + n0 : Y + (m - 1) * p.ylen + n0;
+                        const float2 *P = (m == 0) ? X + xo : Y + (m - 1) * p.ylen;
                         float sr = 0.0f, si = 0.0f;
 #pragma unroll
                         for (int j = 0; j < TS; j++) {
                             int off = j - r;
                             if (off < 0) off += TS;
-                            const float2 vv = P[off];
-                            if (j == 0) { sr = vv.x; si = vv.y; }
-                            else { sr = __fadd_rn(sr, vv.x); si = __fadd_rn(si, vv.y); }
+                            const float2 w = P[wb_phys<SWZ>(n0 + off)];
+                            if (j == 0) { sr = w.x; si = w.y; }
+                            else { sr = __fadd_rn(sr, w.x); si = __fadd_rn(si, w.y); }
                         }
                         f[m] = make_float2(sr, si);
                         const float pw = __fadd_rn(__fmul_rn(sr, sr), __fmul_rn(si, si));
-                        e = (m == 0) ? pw : __fadd_rn(e, pw);        /* reference src/fsk.c:864-867 */
+                        e = (m == 0) ? pw : __fadd_rn(e, pw);
                     }
                 }
                 __syncwarp();
@@ -390,64 +542,65 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 #pragma unroll
                     for (int m = 0; m < M; m++) {
                         float2 *P = (m == 0) ? X + xo : Y + (m - 1) * p.ylen;
-                        P[i] = f[m];
+                        P[wb_phys<SWZ>(i)] = f[m];
                     }
                     E[i] = e;
                 }
                 __syncwarp();
-                r += rinc;
-                if (r >= TS) r -= TS;
             }
         }
         __syncthreads();
 
-        /* ================= B3: warp 0, lane = (re/im, stream): fine-timing accumulation ================= */
-        if (warp == 0) {
-            const int cidx = (lane < spb) ? 0 : 1;
-            const int s = min(lane - cidx * spb, spb - 1);
-            float acc = 0.0f;
-            if (lane < 2 * spb) {
+        /* ================= B3: warp 0, lane = stream: fine-timing accumulation ================= */
+        if (warp == 0 && lane < spb) {
+            wb_fsk_sc &c = sc[lane];
+            if (c.flags & 1) {
                 const float *Es = reinterpret_cast<const float *>(
-                    reinterpret_cast<const float2 *>(regions + (size_t)s * p.sreg) + p.xlen + p.blen);
-                const float *pf = reinterpret_cast<const float *>(p.pft) + cidx;
-                int i = 0;
-#pragma unroll 1
-                for (; i + 8 <= p.nint; i += 8) {
-                    float ev[8], pv[8];
+                    reinterpret_cast<const float2 *>(regions + (size_t)lane * p.sreg) + p.xlen + p.blen);
+                float tcr = 0.0f, tci = 0.0f;
+                if (blocked) {
+                    /* fully unrolled: E positions and the oscillator table (kernel parameters = constant bank)
+                       are immediates; two dependent additions per output is all that is sequential */
 #pragma unroll
-                    for (int j = 0; j < 8; j++) { ev[j] = Es[i + j]; pv[j] = __ldg(pf + 2 * (i + j)); }
+                    for (int i0 = 0; i0 < NBLK * TS; i0 += 14) {
+                        float ev[14];               /* 14 loads in flight, then 14 + 14 dependent additions */
 #pragma unroll
-                    for (int j = 0; j < 8; j++) acc = __fadd_rn(acc, __fmul_rn(ev[j], pv[j]));   /* src/fsk.c:870 */
-                }
-                for (; i < p.nint; i++) acc = __fadd_rn(acc, __fmul_rn(Es[i], __ldg(pf + 2 * i)));
-            }
-            const float tcr = __shfl_sync(0xffffffffu, acc, s);
-            const float tci = __shfl_sync(0xffffffffu, acc, spb + s);
-            if (lane < spb) {
-                wb_fsk_sc &c = sc[s];
-                if (c.flags & 1) {
-                    const bool nan = isnan(tcr) || isnan(tci);     /* reference src/fsk.c:878-880 */
-                    if (!nan) {
-                        const float norm = (float)((double)wb_atan2f(tci, tcr) / 6.283185307179586);
-                        const float rx_timing = __fmul_rn(norm, (float)p.P);
-                        const float dn = __fsub_rn(norm, c.norm);
-                        c.norm = norm;
-                        if ((double)fabsf(dn) < .2) {
-                            const float appm = (float)(1e6 * (double)dn / (double)(float)p.Nsym);
-                            c.ppm = (float)(.9 * (double)c.ppm + .1 * (double)appm);
+                        for (int j = 0; j < 14; j++) ev[j] = Es[((i0 + j) % TS) * NBLK + (i0 + j) / TS];
+#pragma unroll
+                        for (int j = 0; j < 14; j++) {
+                            tcr = __fadd_rn(tcr, __fmul_rn(ev[j], p.pftc[i0 + j].x));          /* reference src/fsk.c:870 */
+                            tci = __fadd_rn(tci, __fmul_rn(ev[j], p.pftc[i0 + j].y));
                         }
-                        if ((double)norm > 0.25) c.nin_next = p.N + p.Ts / 2;
-                        else if ((double)norm < -0.25) c.nin_next = p.N - p.Ts / 2;
-                        else c.nin_next = p.N;
-                        const int low = (int)floorf(rx_timing);
-                        c.low = low;
-                        c.fract = __fsub_rn(rx_timing, (float)low);
-                        c.high = (int)ceilf(rx_timing);
-                        c.rx_timing = rx_timing;
-                    } else {
-                        c.flags = 3;
-                        c.nin_next = c.nin;
                     }
+                } else {
+                    for (int i = 0; i < p.nint; i++) {
+                        const float e = Es[i];
+                        const float2 t2 = p.pftc[i];
+                        tcr = __fadd_rn(tcr, __fmul_rn(e, t2.x));
+                        tci = __fadd_rn(tci, __fmul_rn(e, t2.y));
+                    }
+                }
+                const bool nan = isnan(tcr) || isnan(tci);     /* reference src/fsk.c:878-880 */
+                if (!nan) {
+                    const float norm = (float)((double)wb_atan2f(tci, tcr) / 6.283185307179586);
+                    const float rx_timing = __fmul_rn(norm, (float)p.P);
+                    const float dn = __fsub_rn(norm, c.norm);
+                    c.norm = norm;
+                    if ((double)fabsf(dn) < .2) {
+                        const float appm = (float)(1e6 * (double)dn / (double)(float)p.Nsym);
+                        c.ppm = (float)(.9 * (double)c.ppm + .1 * (double)appm);
+                    }
+                    if ((double)norm > 0.25) c.nin_next = p.N + p.Ts / 2;
+                    else if ((double)norm < -0.25) c.nin_next = p.N - p.Ts / 2;
+                    else c.nin_next = p.N;
+                    const int low = (int)floorf(rx_timing);
+                    c.low = low;
+                    c.fract = __fsub_rn(rx_timing, (float)low);
+                    c.high = (int)ceilf(rx_timing);
+                    c.rx_timing = rx_timing;
+                } else {
+                    c.flags = 3;
+                    c.nin_next = c.nin;
                 }
             }
         }
@@ -456,29 +609,32 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
         /* ================= C: stream warps, lanes = symbols ================= */
         if (active) {
             wb_fsk_sc &c = sc[warp];
-            float *out = sdrow + n_out;
+            int sgw = sgc;
+            asm volatile("" : "+r"(sgw));
+            float *out = WB_ROW_SD(sgw) + n_out;
             if (!(c.flags & 2)) {
                 const int low = c.low, high = c.high;
                 const float fract = c.fract, omf = __fsub_rn(1.0f, fract);
                 for (int i = lane; i < p.Nsym; i += 32) {
                     const int stt = (i + 1) * p.P;
+                    const int il = wb_phys<SWZ>(stt + low), ih = wb_phys<SWZ>(stt + high);
                     float tm[M];
 #pragma unroll
                     for (int m = 0; m < M; m++) {
                         const float2 *fi = (m == 0) ? X + xo : Y + (m - 1) * p.ylen;
-                        const float2 lo = fi[stt + low], hi = fi[stt + high];
+                        const float2 lo = fi[il], hi = fi[ih];
                         const float tr = __fadd_rn(__fmul_rn(omf, lo.x), __fmul_rn(fract, hi.x));
                         const float ti = __fadd_rn(__fmul_rn(omf, lo.y), __fmul_rn(fract, hi.y));
                         tm[m] = __fsqrt_rn(__fadd_rn(__fmul_rn(tr, tr), __fmul_rn(ti, ti)));
                     }
                     if (M == 2) {
-                        out[i] = __fsub_rn(tm[0], tm[1]);                    /* reference src/fsk.c:966 */
+                        __stcs(out + i, __fsub_rn(tm[0], tm[1]));            /* reference src/fsk.c:966 */
                     } else {                                                  /* reference src/fsk.c:969-979 */
                         float b1 = -tm[0], b0 = -tm[0];
                         b1 = __fadd_rn(b1, tm[1]);  b0 = __fadd_rn(b0, -tm[1]);
                         b1 = __fadd_rn(b1, -tm[2]); b0 = __fadd_rn(b0, tm[2]);
                         b1 = __fadd_rn(b1, tm[3]);  b0 = __fadd_rn(b0, tm[3]);
-                        out[2 * i + 1] = b1; out[2 * i] = b0;
+                        __stcs(out + 2 * i + 1, b1); __stcs(out + 2 * i, b0);
                     }
                 }
             } else {
@@ -488,10 +644,8 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                     out[i] = (n_out >= (unsigned)p.Nbits) ? out[i - p.Nbits] : 0.0f;
             }
             __syncwarp();
-            /* samp_old for the next frame */
-#pragma unroll
-            for (int q = 0; q < WB_NST; q++)
-                if (lane + 32 * q < nstash) X[lane + 32 * q] = stash[q];
+            /* old samples for the next frame */
+            if (lane < nst) X[lane] = stash;
             if (lane == 0) {
 #pragma unroll
                 for (int m = 0; m < M; m++) c.pb[m] = c.nb[m];              /* fsk->f_est = this frame's, :846 */
@@ -516,9 +670,8 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 #pragma unroll
         for (int q = 0; q < WB_NEQ; q++)
             if (lane + 32 * q < nh) st->fft_est[lane + 32 * q] = est[q];
-#pragma unroll
-        for (int q = 0; q < WB_NST; q++)
-            if (lane + 32 * q < nstash) st->samp_old[lane + 32 * q] = X[lane + 32 * q];
+        if (lane < nst) st->samp_old[lane] = X[lane];
+        const unsigned char *in = WB_ROW_IN(sg);
         const unsigned long long rem = fill - pos;
         const unsigned long long dstpos = (unsigned long long)a.headroom - rem;   /* remainder ends at the headroom mark */
         if (a.compact && rem > 0 && pos > dstpos) {
@@ -527,7 +680,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                dst < src, ascending copy through registers. */
             const int bps = p.in_bps;
             unsigned char *row = const_cast<unsigned char *>(in);
-            const unsigned long long nbytes = rem * bps, sb = pos * bps, db = dstpos * bps;
+            const unsigned long long nbytes = rem * bps, sb = (unsigned long long)pos * bps, db = dstpos * bps;
             for (unsigned long long off = 0; off < nbytes; off += 32 * 8) {
                 unsigned char tmp[8];
                 const unsigned long long o = off + (unsigned long long)lane * 8;
@@ -547,7 +700,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             else { st->in_pos = pos; st->in_fill = fill; }
             wb_cursor &cu = a.cursor[sg];
             cu.in_fill = rem;
-            cu.consumed = pos - pos0;
+            cu.consumed = (unsigned long long)(pos - pos0);
             cu.n_sd = n_out;
             cu.nin = nin;
         }

@@ -25,6 +25,7 @@
 #define WB_MAX_NSTASH (4 * WB_MAX_TS)
 #define WB_MAX_NIN 512                 /* N + Ts/2 must not exceed this */
 #define WB_MAX_LEVELS 8
+#define WB_MAX_NINT 496                /* (Nsym + 1) * P <= 49 * 10, rounded */
 #define WB_FRAME_SYMS 48               /* nsyms, reference src/fsk.c:134 */
 #define WB_FSK_THREADS 512             /* 16 stream-warps (2-FSK) / 8 stream-warps x 2 CTAs' worth (4-FSK: 256) */
 
@@ -37,6 +38,7 @@
 
 struct wb_fsk_params {
     int Fs, Rs, Ts, P, M, N, Nsym, Nmem, Nbits, Ndft, nstash;
+    int nst;                  /* 2*Ts + Ts/2: old samples the mixer can reach back to (<= nstash = 4*Ts) */
     int step;                 /* Ts / P */
     int nint;                 /* (Nsym + 1) * P integrator outputs per frame */
     int nsteps;               /* Nmem - step mixer steps per frame */
@@ -44,7 +46,7 @@ struct wb_fsk_params {
     int f_min, f_max, f_zero; /* estimator bin limits, reference src/fsk.c:568-570 */
     float tc;                 /* 0.95 * Ndft / Fs, reference src/fsk.c:573 */
     int n_levels;             /* FFT schedule, leaf first */
-    int lev_p[WB_MAX_LEVELS], lev_m[WB_MAX_LEVELS], lev_fstride[WB_MAX_LEVELS];
+    int lev_p[WB_MAX_LEVELS], lev_m[WB_MAX_LEVELS], lev_fstride[WB_MAX_LEVELS], lev_sh[WB_MAX_LEVELS];
     int in_fmt, in_bps;       /* bytes per input sample */
     int xlen, ylen, blen, sreg; /* smem geometry per stream: float2 of X, of one other-tone buffer, of all of them
                                   (>= Ndft: FFT work buffer); bytes per stream region (== 8 mod 16) */
@@ -55,6 +57,9 @@ struct wb_fsk_params {
     const float2 *pft;        /* [nint]       fine-timing oscillator, reference src/fsk.c:858-873 */
     const float2 *dphi;       /* [Ndft/2]     comp_exp_j(2 pi f/Fs), f = bin*Fs/Ndft, src/fsk.c:763 */
     const float2 *back;       /* [3][Ndft/2]  phase back-off for nin = N-Ts/2, N, N+Ts/2, src/fsk.c:758 */
+    /* the fine-timing oscillator again, by value: kernel parameters live in the constant bank, which is the
+       right home for a table every lane reads at the same index */
+    float2 pftc[WB_MAX_NINT];
 };
 
 struct wb_stream_state {
