@@ -115,6 +115,9 @@ int  wb_feed_strided(wb_engine *e, const void *base, uint64_t stride_bytes, uint
    (fsk_demod.c:299), then the UW search / collect / sd_to_llr / run_ldpc_decoder / CRC gate of
    drs232_ldpc.c:176-259.  Asynchronous; the drain calls and wb_sync wait for it. */
 int  wb_process(wb_engine *e);
+/* the same without a demodulator in front: the fread(&symbol) loop of drs232_ldpc.c:176 / wenet_ldpc.c:171.
+   sd[s] = nsym[s] float32 soft symbols (negative = 1) of stream s, at most sd_cap (wb_geometry) per call */
+int  wb_process_soft(wb_engine *e, const float *const *sd, const uint64_t *nsym);
 int  wb_sync(wb_engine *e);
 /* the fwrite(packet) of drs232_ldpc.c:254: CRC-valid 256-byte payloads of `stream`, decode order,
    produced since the last drain of that stream */

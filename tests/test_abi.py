@@ -1,0 +1,75 @@
+"""The C-ABI library: builds, loads, exports every symbol include/wenet_b200.h declares, and refuses to run
+without a GPU (no CPU fallback).  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from wenet_b200 import engine
+    return engine.load_library()
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "wenet_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(wb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_and_binding_agree(lib):
+    from wenet_b200 import engine
+    decl = declared_symbols()
+    bound = sorted(n for n, _, _ in engine.ABI)
+    assert decl == bound, (set(decl) ^ set(bound))
+    for name in decl:
+        assert hasattr(lib, name), name
+    assert lib.wb_abi_version() == 1
+
+
+def test_struct_layouts_match_header(lib):
+    from wenet_b200 import engine
+    assert C.sizeof(engine.WbConfig) == 64
+    assert engine.CODEWORD_DTYPE.itemsize == 280
+    assert C.sizeof(engine.WbStats) == 4 * 9 + 4 * 3 + 4 * 8 * 160 + 4 + 4 * 512 + 8 + 8 + 4   # incl. alignment pad
+
+
+def test_no_gpu_means_no_engine(lib):
+    """on a machine without CUDA the engine must fail loudly (WB_ENODEV), never fall back to a CPU path"""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    from wenet_b200 import engine
+    with pytest.raises(engine.WbError) as ei:
+        engine.Engine(1, chunk_samples=4096)
+    assert ei.value.code == engine.WB_ENODEV
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_bad_arguments_are_errors_not_aborts(lib):
+    from wenet_b200 import engine
+    cfg = engine.WbConfig()
+    h = C.c_void_p()
+    assert lib.wb_create(C.byref(cfg), C.byref(h)) == engine.WB_EINVAL        # struct_size = 0
+    assert b"struct_size" in lib.wb_last_error()
+    assert lib.wb_create(None, C.byref(h)) == engine.WB_EINVAL
+    assert lib.wb_process(None) == engine.WB_EINVAL
+
+
+def test_product_never_imports_the_oracle():
+    """the product package must not reference oracle/ (parity claims depend on it)"""
+    pkg = os.path.join(ROOT, "wenet_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".c")) and f != "wb_tables.h":
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "liboracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f

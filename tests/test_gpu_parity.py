@@ -245,3 +245,80 @@ def test_many_streams_one_launch(eng_mod, oracle_port):
         assert np.array_equal(sd_g.view(np.uint32), sd_o.view(np.uint32)), s
         assert e.drain_packets(s) == res_o["packets"], s
     e.close()
+
+
+def test_process_soft_vs_oracle(eng_mod, oracle_port):
+    """the drs232_ldpc / wenet_ldpc entry point: soft symbols in (ragged blocks, packets straddling calls)"""
+    for framing, cfg in (("v1", siggen.V1), ("v2", siggen.V2)):
+        rng = np.random.default_rng(9)
+        sds = []
+        for s in range(3):
+            raw, _ = siggen.make_stream(70 + s, n_packets=3, ebno_db=8.0 + s, framing=framing, fmt="cf32")
+            sd, _, _ = oracle_port.fsk(cfg["Fs"], cfg["Rs"]).run(raw, "cf32")
+            sds.append(np.concatenate([sd, rng.standard_normal(3000).astype(np.float32)]))
+        refs = [oracle_port.deframer(framing, 10).feed(sd) for sd in sds]
+        e = eng_mod.Engine(3, Fs=cfg["Fs"], Rs=cfg["Rs"], framing=framing, chunk_samples=1 << 16)
+        pos, got, iters = [0] * 3, [b""] * 3, [[] for _ in range(3)]
+        while any(pos[s] < sds[s].size for s in range(3)):
+            blk = []
+            for s in range(3):
+                n = int(rng.integers(0, 5000))
+                blk.append(sds[s][pos[s]:pos[s] + n])
+                pos[s] += len(blk[-1])
+            e.process_soft(blk)
+            e.sync()
+            for cw in e.drain_codewords():
+                iters[cw["stream"]].append(int(cw["iters"]))
+            for s in range(3):
+                got[s] += e.drain_packets(s)
+        for s in range(3):
+            assert got[s] == refs[s]["packets"], (framing, s)
+            assert iters[s] == refs[s]["iters"].tolist(), (framing, s)
+        e.close()
+
+
+def test_cli_pipe_matches_reference_bytes():
+    """python -m wenet_b200.cli.fsk_demod --cu8 -s ... | python -m wenet_b200.cli.drs232_ldpc - -  against the bytes
+    the reference CLIs produced for the same input (tests/golden/fsk_v1.npz, made by tools/gen_golden.py)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root)
+    z = np.load(os.path.join(GOLD, "fsk_v1.npz"))
+    sd = subprocess.run([sys.executable, "-m", "wenet_b200.cli.fsk_demod", "--cu8", "-s", "2", "921416", "115177", "-", "-"],
+                        input=z["raw"].tobytes(), stdout=subprocess.PIPE, env=env, check=True, timeout=300).stdout
+    assert sd == z["sd"].tobytes()
+    r = subprocess.run([sys.executable, "-m", "wenet_b200.cli.drs232_ldpc", "-", "-", "-v"], input=sd, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, env=env, check=True, timeout=300)
+    assert r.stdout == z["packets"].tobytes()
+    assert b"packets: 2 packet_errors: 0 PER: 0.000" in r.stderr
+    fused = subprocess.run([sys.executable, "-m", "wenet_b200.cli.wenet_rx", "--cu8", "-", "-"], input=z["raw"].tobytes(),
+                           stdout=subprocess.PIPE, env=env, check=True, timeout=300).stdout
+    assert fused == z["packets"].tobytes()
+    z2 = np.load(os.path.join(GOLD, "fsk_v2.npz"))
+    sd2 = subprocess.run([sys.executable, "-m", "wenet_b200.cli.fsk_demod", "--cs16", "-s", "2", "960000", "96000", "-", "-"],
+                         input=z2["raw"].tobytes(), stdout=subprocess.PIPE, env=env, check=True, timeout=300).stdout
+    assert sd2 == z2["sd"].tobytes()
+    pk2 = subprocess.run([sys.executable, "-m", "wenet_b200.cli.wenet_ldpc", "-", "-"], input=sd2, stdout=subprocess.PIPE,
+                         env=env, check=True, timeout=300).stdout
+    assert pk2 == z2["packets"].tobytes()
+
+
+def test_golden_vectors_through_the_engine(eng_mod):
+    """the committed reference outputs, straight against the CUDA path (no oracle in between)"""
+    z = np.load(os.path.join(GOLD, "ldpc_llr.npz"))
+    e = eng_mod.Engine(1, framing="v1", chunk_samples=4096)
+    llr = e.sd_to_llr_batch(z["sd"])
+    assert np.array_equal(llr.view(np.uint32), z["llr"].view(np.uint32))
+    for mi in (10, 100):
+        bits, iters, pcc = e.ldpc_decode_batch(z["llr"], max_iter=mi)
+        assert np.array_equal(iters, z["iters%d" % mi]) and np.array_equal(pcc, z["pcc%d" % mi])
+        assert np.array_equal(np.packbits(bits, axis=1), z["bits%d" % mi])
+    e.close()
+    z4 = np.load(os.path.join(GOLD, "fsk_4fsk.npz"))
+    e = eng_mod.Engine(1, M=4, in_fmt="cu8", framing="none", chunk_samples=z4["raw"].size // 2 + 1024)
+    e.feed([z4["raw"]])
+    e.process()
+    e.sync()
+    assert np.array_equal(e.drain_soft(0).view(np.uint32), z4["sd"].view(np.uint32))
+    e.close()

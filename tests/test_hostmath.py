@@ -1,0 +1,65 @@
+"""Scalar numeric building blocks of the CUDA kernels (wenet_b200/csrc/wb_math.h, wb_phi0.h), compiled for the
+host as libwb_hostmath.so: they must equal what the reference's x86-64 build computes -- glibc atan2f, the x87
+long-double expressions of sd_to_llr (src/mpdecode_core.c:593-595) and the phi0 compare tree (src/phi0.c)."""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "wenet_b200", "libwb_hostmath.so")
+
+
+@pytest.fixture(scope="module")
+def hm():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "wenet_b200", "csrc"), "../libwb_hostmath.so"])
+    return C.CDLL(SO)
+
+
+def _call(fn, *arrays_in, out_dtype):
+    n = arrays_in[0].size
+    out = np.empty(n, dtype=out_dtype)
+    fn(*[a.ctypes.data_as(C.c_void_p) for a in arrays_in], out.ctypes.data_as(C.c_void_p), C.c_long(n))
+    return out
+
+
+def test_atan2f_equals_glibc(hm):
+    libm = C.CDLL("libm.so.6")
+    libm.atan2f.restype = C.c_float
+    libm.atan2f.argtypes = [C.c_float, C.c_float]
+    rng = np.random.default_rng(0)
+    y = np.concatenate([rng.standard_normal(200000) * 10 ** rng.uniform(-6, 6, 200000),
+                        [0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-38, 3e38]]).astype(np.float32)
+    x = np.concatenate([rng.standard_normal(200000) * 10 ** rng.uniform(-6, 6, 200000),
+                        [1.0, -1.0, 0.0, -0.0, np.inf, 1.0, 1.0, -3e38, 1e-38]]).astype(np.float32)
+    got = _call(hm.wbh_atan2f, y, x, out_dtype=np.float32)
+    ref = np.array([libm.atan2f(float(a), float(b)) for a, b in zip(y, x)], dtype=np.float32)
+    same = (got.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(got) & np.isnan(ref))
+    assert same.all(), np.nonzero(~same)[0][:5]
+
+
+def test_x87_emulation(hm):
+    rng = np.random.default_rng(1)
+    v = np.concatenate([10 ** rng.uniform(-9, 3, 300000), [0.0, 1e-3, 0.5, 2.0 ** -20]])
+    a = _call(hm.wbh_esn0_from_var, v, out_dtype=np.float64)
+    b = _call(hm.wbh_esn0_from_var_x87, v, out_dtype=np.float64)
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    c = 4.0 * 10 ** rng.uniform(-3, 3, 300000)
+    sd = (rng.standard_normal(300000) * 10 ** rng.uniform(-4, 2, 300000)).astype(np.float32)
+    a = _call(hm.wbh_llr_scale, c, sd, out_dtype=np.float32)
+    b = _call(hm.wbh_llr_scale_x87, c, sd, out_dtype=np.float32)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_phi0_tables(hm, oracle_port):
+    rng = np.random.default_rng(2)
+    x = np.concatenate([rng.uniform(-1, 40, 500000), 2.0 ** rng.uniform(-20, 17, 500000),
+                        [0.0, -0.0, np.nan, np.inf, -np.inf, 32768, 32767.99, 1e9, 10, 9.9999]]).astype(np.float32)
+    ref = oracle_port.phi0(x)
+    for name in ("wbh_phi0", "wbh_phi0_compact"):
+        got = _call(getattr(hm, name), x, out_dtype=np.float32)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), name
+    assert math.isclose(float(oracle_port.phi0(np.float32([0.5]))[0]), 1.5735153, rel_tol=1e-7)

@@ -1,0 +1,93 @@
+"""Differential tests: the C restatement (oracle/liboracle.so) against the UNMODIFIED reference compiled from
+/root/reference/src into oracle/_ref (library taps through oracle/ref_harness.c, deframers through the real
+CLI binaries over pipes).  Skipped where oracle/_ref has not been built; tests/test_golden.py covers that case
+with committed vectors."""
+import numpy as np
+import pytest
+
+from wenet_b200 import siggen
+
+
+def test_phi0_sweep(oracle_port, oracle_ref):
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-1, 40, 300000), 2.0 ** rng.uniform(-20, 17, 300000),
+                        [0.0, -0.0, np.nan, np.inf, -np.inf, 32768, 32767.99, 1e9]]).astype(np.float32)
+    assert np.array_equal(oracle_port.phi0(x).view(np.uint32), oracle_ref.phi0(x).view(np.uint32))
+
+
+def test_sd_to_llr(oracle_port, oracle_ref):
+    rng = np.random.default_rng(1)
+    for k in range(30):
+        sd = (rng.choice([-1.0, 1.0], 2580) * rng.uniform(0.05, 40) + rng.standard_normal(2580) * rng.uniform(0.01, 3)
+              ).astype(np.float32).astype(np.float64)
+        assert np.array_equal(oracle_port.sd_to_llr(sd).view(np.uint32), oracle_ref.sd_to_llr(sd).view(np.uint32)), k
+
+
+@pytest.mark.parametrize("max_iter", [10, 100])
+def test_ldpc_decode(oracle_port, oracle_ref, max_iter):
+    rng = np.random.default_rng(2)
+    for k in range(24):
+        data = rng.integers(0, 2, 2064, dtype=np.uint8)
+        if k % 6 == 5:
+            data[:] = 0
+        par = oracle_ref.ldpc_encode(data)
+        assert np.array_equal(par, oracle_port.ldpc_encode(data))
+        cw = np.concatenate([data, par]).astype(np.float64)
+        sd = (1 - 2 * cw) * rng.uniform(0.3, 3) + 10 ** (-rng.uniform(0, 8) / 20) * rng.standard_normal(2580)
+        llr = oracle_ref.sd_to_llr(sd.astype(np.float32).astype(np.float64))
+        a, b = oracle_port.ldpc_decode(llr, max_iter, -1), oracle_ref.ldpc_decode(llr, max_iter, -1)
+        assert a[1] == b[1] and a[2] == b[2] and np.array_equal(a[0], b[0]), k
+
+
+FSK_CASES = [("cf32", 2, None, siggen.V1, 9.0, 0.0), ("cs16", 2, None, siggen.V1, 7.0, 3000.0),
+             ("cu8", 2, None, siggen.V1, 12.0, -2500.0), ("cf32", 2, None, siggen.V2, 9.0, 1500.0),
+             ("cf32", 2, 4, siggen.V1, 10.0, 0.0), ("cs16", 2, 5, siggen.V2, 10.0, 0.0)]
+
+
+@pytest.mark.parametrize("fmt,M,P,cfg,ebno,ppm", FSK_CASES)
+def test_fsk_stream(oracle_port, oracle_ref, fmt, M, P, cfg, ebno, ppm):
+    framing = "v1" if cfg is siggen.V1 else "v2"
+    raw, _ = siggen.make_stream(11, n_packets=2, ebno_db=ebno, framing=framing, fmt=fmt, clock_ppm=ppm)
+    a = oracle_port.fsk(cfg["Fs"], cfg["Rs"], M=M, P=P)
+    b = oracle_ref.fsk(cfg["Fs"], cfg["Rs"], M=M, P=P)
+    sa, la, ca = a.run(raw, fmt)
+    sb, lb, cb = b.run(raw, fmt)
+    assert ca == cb and np.array_equal(sa.view(np.uint32), sb.view(np.uint32))
+    assert np.array_equal(la[:, :3].view(np.uint32), lb[:, :3].view(np.uint32))       # nin, f_est[0..1]
+    assert np.array_equal(la[:, 5:].view(np.uint32), lb[:, 5:].view(np.uint32))       # norm_rx_timing, ppm, EbNodB
+    assert np.array_equal(a.state()[:2 * M], b.state()[:2 * M])                        # phi_c
+    assert np.array_equal(a.fft_est().view(np.uint32), b.fft_est().view(np.uint32))
+    # (the eye-diagram tap of the stats surface, SURVEY 8f2, is not on the hot path and not pinned here)
+
+
+def test_fsk_4fsk(oracle_port, oracle_ref):
+    raw, _ = siggen.make_4fsk_stream(5, 4000, ebno_db=9.0, fmt="cs16")
+    sa, la, _ = oracle_port.fsk(921416, 115177, M=4).run(raw, "cs16")
+    sb, lb, _ = oracle_ref.fsk(921416, 115177, M=4).run(raw, "cs16")
+    assert np.array_equal(sa.view(np.uint32), sb.view(np.uint32)) and np.array_equal(la.view(np.uint32), lb.view(np.uint32))
+
+
+@pytest.mark.parametrize("framing", ["v1", "v2"])
+def test_deframer_vs_cli(oracle_port, oracle_ref, framing):
+    """deframer + sd_to_llr + decoder + CRC gate against the real drs232_ldpc / wenet_ldpc binaries, incl.
+    noise-only stretches (false unique-word hits) and a marginal SNR"""
+    from oracle import oracle as O
+    cfg = siggen.V1 if framing == "v1" else siggen.V2
+    rng = np.random.default_rng(3)
+    parts = []
+    for s, ebno in enumerate([7.5, 8.0, 10.0]):
+        raw, _ = siggen.make_stream(30 + s, n_packets=3, ebno_db=ebno, framing=framing, fmt="cf32")
+        sd, _, _ = oracle_port.fsk(cfg["Fs"], cfg["Rs"]).run(raw, "cf32")
+        parts += [sd, rng.standard_normal(5000).astype(np.float32)]
+    sd = np.concatenate(parts)
+    res = oracle_port.deframer(framing, 10).feed(sd)
+    assert res["packets"] == O.run_ref_deframer(sd, framing)
+    assert 3 <= len(res["packets"]) // 256 <= 9
+
+
+def test_full_pipe_vs_cli(oracle_port, oracle_ref):
+    from oracle import oracle as O
+    raw, payloads = siggen.make_stream(40, n_packets=3, ebno_db=10.0, fmt="cs16", clock_ppm=1000.0)
+    sd, _, _ = oracle_port.fsk(921416, 115177).run(raw, "cs16")
+    out = oracle_port.deframer("v1", 10).feed(sd)["packets"]
+    assert out == O.run_ref_pipe(raw.tobytes(), fmt="cs16") == b"".join(payloads)

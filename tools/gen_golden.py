@@ -1,0 +1,94 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz from the UNMODIFIED reference compiled under oracle/_ref.
+
+Runs only in the build container (needs /root/reference to have been compiled by `make -C oracle ref`).
+The outputs are committed; tests never read /root/reference.
+
+  fsk_v1.npz    cu8 IQ of one seeded v1 stream -> reference `fsk_demod --cu8 -s 2 921416 115177` soft decisions
+                and `| drs232_ldpc` packet bytes (the real CLIs over pipes), plus the harness' nin sequence
+  fsk_v2.npz    cs16 IQ of one v2 stream (Fs 960000 / Rs 96000) -> fsk_demod --cs16 -s | wenet_ldpc
+  fsk_4fsk.npz  cu8 IQ of an unframed 4-FSK stream -> fsk_demod --cu8 -s 4 921416 115177 soft decisions
+  ldpc_llr.npz  soft-decision blocks -> reference sd_to_llr() LLRs -> run_ldpc_decoder() bits / iterations / parity
+                counts for max_iter 10 and 100
+  phi0.npz      arguments around every breakpoint (+ specials) -> reference phi0()
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O          # noqa: E402
+from wenet_b200 import siggen           # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def cli(args, data):
+    return subprocess.run(args, input=data, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+
+
+def main():
+    ref = O.Oracle("reference")
+    fsk_demod, drs, wen = O.ref_cli("fsk_demod"), O.ref_cli("drs232_ldpc"), O.ref_cli("wenet_ldpc")
+    os.makedirs(GOLD, exist_ok=True)
+
+    raw, payloads = siggen.make_stream(7, n_packets=2, ebno_db=9.0, fmt="cu8", clock_ppm=2000.0)
+    sd = cli([fsk_demod, "--cu8", "-s", "2", "921416", "115177", "-", "-"], raw.tobytes())
+    pk = cli([drs, "-", "-"], sd)
+    _, log, _ = ref.fsk(921416, 115177).run(raw, "cu8")
+    np.savez_compressed(os.path.join(GOLD, "fsk_v1.npz"), raw=raw, sd=np.frombuffer(sd, np.float32),
+                        packets=np.frombuffer(pk, np.uint8), nin=log[:, 0].astype(np.int16),
+                        payloads=np.frombuffer(b"".join(payloads), np.uint8))
+
+    raw, payloads = siggen.make_stream(8, n_packets=2, ebno_db=10.0, framing="v2", fmt="cs16", clock_ppm=-1500.0)
+    sd = cli([fsk_demod, "--cs16", "-s", "2", "960000", "96000", "-", "-"], raw.tobytes())
+    pk = cli([wen, "-", "-"], sd)
+    np.savez_compressed(os.path.join(GOLD, "fsk_v2.npz"), raw=raw, sd=np.frombuffer(sd, np.float32),
+                        packets=np.frombuffer(pk, np.uint8), payloads=np.frombuffer(b"".join(payloads), np.uint8))
+
+    raw, sym = siggen.make_4fsk_stream(9, 2000, ebno_db=10.0, fmt="cu8")
+    sd = cli([fsk_demod, "--cu8", "-s", "4", "921416", "115177", "-", "-"], raw.tobytes())
+    np.savez_compressed(os.path.join(GOLD, "fsk_4fsk.npz"), raw=raw, sd=np.frombuffer(sd, np.float32),
+                        symbols=sym.astype(np.uint8))
+
+    rng = np.random.default_rng(2024)
+    sds, llrs, res = [], [], {10: [], 100: []}
+    for k, snr in enumerate([0.5, 1.5, 2.0, 2.5, 3.0, 4.0, 6.0, 9.0]):
+        data = rng.integers(0, 2, 2064, dtype=np.uint8)
+        if k == 5:
+            data[:] = 0
+        cw = np.concatenate([data, ref.ldpc_encode(data)]).astype(np.float64)
+        s = ((1 - 2 * cw) * rng.uniform(0.3, 3.0) + 10 ** (-snr / 20) * rng.standard_normal(2580)).astype(np.float32)
+        llr = ref.sd_to_llr(s.astype(np.float64))
+        sds.append(s); llrs.append(llr)
+        for mi in (10, 100):
+            bits, it, pcc = ref.ldpc_decode(llr, max_iter=mi, pcc_init=-1)
+            res[mi].append((np.packbits(bits), it, pcc))
+    np.savez_compressed(os.path.join(GOLD, "ldpc_llr.npz"), sd=np.stack(sds), llr=np.stack(llrs),
+                        bits10=np.stack([r[0] for r in res[10]]), iters10=np.array([r[1] for r in res[10]], np.int32),
+                        pcc10=np.array([r[2] for r in res[10]], np.int32),
+                        bits100=np.stack([r[0] for r in res[100]]), iters100=np.array([r[1] for r in res[100]], np.int32),
+                        pcc100=np.array([r[2] for r in res[100]], np.int32))
+
+    z = np.load(os.path.join(ROOT, "wenet_b200", "data", "h2064_516.npz"))
+    xs = [0.0, -0.0, -1.0, 1e-6, 8.6e-5, 0.5, 1.0, 5.0, 9.999, 10.0, 16.0, 32767.9, 32768.0, 1e9, np.inf, np.nan]
+    brk = z["phi0_brk"] if "phi0_brk" in z.files else None
+    if brk is None:
+        import re
+        txt = open(os.path.join(ROOT, "wenet_b200", "csrc", "wb_tables.h")).read()
+        body = txt[txt.index("wb_phi0_brk[103] = {") + 20:]
+        brk = np.array([int(v) for v in re.findall(r"-?\d+", body[:body.index("}")])])
+    for b in brk:
+        v = np.float32(b / 65536.0)
+        xs += [np.nextafter(v, np.float32(-np.inf)), v, np.nextafter(v, np.float32(np.inf))]
+    x = np.array(xs, dtype=np.float32)
+    np.savez_compressed(os.path.join(GOLD, "phi0.npz"), x=x, y=ref.phi0(x))
+    for f in sorted(os.listdir(GOLD)):
+        print(f, os.path.getsize(os.path.join(GOLD, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,53 @@
+"""shared body of the drs232_ldpc / wenet_ldpc stand-ins (reference src/drs232_ldpc.c:105-286, src/wenet_ldpc.c)"""
+import sys
+
+import numpy as np
+
+BLOCK_SYMS = 1 << 15
+
+
+def main(argv, framing, name):
+    if len(argv) < 3:
+        sys.stderr.write("usage: %s InputOneSymbolPerFloat OutputPackets [-v[v]]\n" % name)
+        sys.exit(1)
+    try:
+        fin = sys.stdin.buffer if argv[1] == "-" else open(argv[1], "rb")
+    except OSError as e:
+        sys.stderr.write("Error opening input file: %s: %s.\n" % (argv[1], e.strerror))
+        sys.exit(1)
+    try:
+        fout = sys.stdout.buffer if argv[2] == "-" else open(argv[2], "wb")
+    except OSError as e:
+        sys.stderr.write("Error opening output file: %s: %s.\n" % (argv[2], e.strerror))
+        sys.exit(1)
+    verbose = 1 if (len(argv) > 3 and argv[3] in ("-v", "-vv")) else 0
+    from wenet_b200 import engine as E
+    try:
+        eng = E.Engine(1, framing=framing, chunk_samples=BLOCK_SYMS * 16)
+    except E.WbError as e:
+        sys.stderr.write("%s\n" % e)
+        sys.exit(1)
+    packets = errors = 0
+    while True:
+        raw = fin.read(4 * min(BLOCK_SYMS, eng.sd_cap))
+        if not raw:
+            break
+        raw = raw[:len(raw) - len(raw) % 4]
+        eng.process_soft([np.frombuffer(raw, dtype=np.float32)])
+        eng.sync()
+        for cw in eng.drain_codewords():
+            packets = (packets + 1) & 0xFFFF                     # uint16_t counters, src/drs232_ldpc.c:116
+            if not cw["crc_ok"]:
+                errors = (errors + 1) & 0xFFFF
+            if verbose:
+                sys.stderr.write("packets: %d packet_errors: %d PER: %4.3f iter: %d\n"
+                                 % (packets, errors, errors / packets if packets else float("nan"), cw["iters"]))
+        pk = eng.drain_packets(0)
+        if pk:
+            fout.write(pk)
+            fout.flush()
+    fout.flush()
+    sys.stderr.write("packets: %d packet_errors: %d PER: %4.3f\n"
+                     % (packets, errors, errors / packets if packets else float("nan")))
+    eng.close()
+    return 0

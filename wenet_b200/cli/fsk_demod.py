@@ -1,0 +1,149 @@
+#!/usr/bin/env python3
+"""fsk_demod [-l] [-p P] [-s] [(-c|-d)] [-t[r]] [-f] [-b lo] [-u hi] (2|4) SampleRate SymbolRate In Out
+
+Same argv, input formats, output stream and exit codes as reference src/fsk_demod.c:89-206, demodulating on the
+GPU through libwenet_b200.so.  Differences, all outside the hot path: -l (low-rate mode) and -f (test frames)
+are not implemented and exit 1; the stats JSON (stderr, -t) carries the keys rx/fskstatsudp.py needs
+(EbNodB, ppm, f1_est, f2_est, samp_fft) with EbNodB estimated from the soft decisions and an empty eye diagram;
+without -s the hard bits are the signs of the soft decisions.  Output is written per block of frames, not per frame.
+"""
+import getopt
+import json
+import math
+import signal
+import sys
+import time
+
+import numpy as np
+
+USAGE = ("usage: %s [-l] [-p P]  [-s] [(-c|-d)] [-t [r]] [-f] (2|4) SampleRate SymbolRate InputModemRawFile OutputFile\n"
+         " -p P --conv=P     -  P specifies the rate at which symbols are down-converted before further processing\n"
+         " -c --cs16         -  The raw input file will be in complex signed 16 bit format.\n"
+         " -d --cu8          -  The raw input file will be in complex unsigned 8 bit format.\n"
+         "                        If neither -c nor -d are used, the input should be in signed 16 bit format.\n"
+         " -t[r] --stats=[r] -  Print out modem statistics to stderr in JSON.\n"
+         " -s --soft-dec     -  The output file will be in a soft-decision format, with one 32-bit float per bit.\n"
+         " -b lo -u hi       -  frequency estimator limits in Hz\n")
+
+BLOCK_FRAMES = 64
+
+
+def usage(prog, msg=None):
+    if msg:
+        sys.stderr.write(msg + "\n")
+    sys.stderr.write(USAGE % prog)
+    sys.exit(1)
+
+
+def parse(argv):
+    try:
+        opts, args = getopt.gnu_getopt(argv[1:], "fhlp:cdt::sb:u:",
+                                       ["help", "lbr", "conv=", "cs16", "cu8", "fsk_lower=", "fsk_upper=", "stats=",
+                                        "stats", "soft-dec", "testframes"])
+    except getopt.GetoptError as e:
+        usage(argv[0], str(e))
+    o = dict(fmt="s16", soft=False, stats=False, stats_rate=8, P=0, lo=0, hi=0)
+    for k, v in opts:
+        if k in ("-h", "--help"):
+            usage(argv[0])
+        elif k in ("-l", "--lbr"):
+            usage(argv[0], "low-rate mode (-l) is not supported by the B200 engine")
+        elif k in ("-f", "--testframes"):
+            usage(argv[0], "testframe mode (-f) is not supported by the B200 engine")
+        elif k in ("-c", "--cs16"):
+            o["fmt"] = "cs16"
+        elif k in ("-d", "--cu8"):
+            o["fmt"] = "cu8"
+        elif k in ("-s", "--soft-dec"):
+            o["soft"] = True
+        elif k in ("-p", "--conv"):
+            o["P"] = int(v)
+        elif k in ("-b", "--fsk_lower"):
+            o["lo"] = int(v or 0)
+        elif k in ("-u", "--fsk_upper"):
+            o["hi"] = int(v or 0)
+        elif k in ("-t", "--stats"):
+            o["stats"] = True
+            if v:
+                try:
+                    o["stats_rate"] = int(v) or 8
+                except ValueError:
+                    o["stats_rate"] = 8
+    if len(args) < 5:
+        usage(argv[0], "Too few arguments")
+    if len(args) > 5:
+        usage(argv[0], "Too many arguments")
+    try:
+        o["M"], o["Fs"], o["Rs"] = int(args[0]), int(args[1]), int(args[2])
+    except ValueError:
+        usage(argv[0], "Mode, SampleRate and SymbolRate must be integers")
+    if o["M"] not in (2, 4):
+        usage(argv[0], "Mode %d is not valid. Mode must be 2 or 4." % o["M"])
+    o["fin"], o["fout"] = args[3], args[4]
+    return o
+
+
+def main(argv=None):
+    argv = argv or sys.argv
+    o = parse(argv)
+    from wenet_b200 import engine as E
+    try:
+        fin = sys.stdin.buffer if o["fin"] == "-" else open(o["fin"], "rb")
+        fout = sys.stdout.buffer if o["fout"] == "-" else open(o["fout"], "wb")
+    except OSError:
+        sys.stderr.write("Couldn't open files\n")
+        sys.exit(1)
+    limits = (o["lo"], o["hi"]) if (o["lo"] > 0 and o["hi"] > o["lo"]) else None
+    try:
+        eng = E.Engine(1, Fs=o["Fs"], Rs=o["Rs"], M=o["M"], P=o["P"], in_fmt=o["fmt"], framing="none",
+                       chunk_samples=(BLOCK_FRAMES + 2) * 512, est_limits=limits)
+    except E.WbError as e:
+        sys.stderr.write("Couldn't open files\n%s\n" % e)
+        sys.exit(1)
+    if limits:
+        sys.stderr.write("Setting estimator limits to %d to %d Hz.\n" % limits)
+    signal.signal(signal.SIGTERM, lambda *_: sys.exit(0))
+    bps = E.FMT_BPS[o["fmt"]]
+    dt = E.FMT_DTYPE[o["fmt"]]
+    stats_every = int(1 / (o["stats_rate"] * eng.N / o["Fs"])) + 1 if o["stats"] else 0
+    frames_since = 0
+    snr_est = 0.0
+    while True:
+        raw = fin.read(BLOCK_FRAMES * eng.N * bps)
+        if not raw:
+            break
+        raw = raw[:len(raw) - len(raw) % bps]
+        eng.feed([np.frombuffer(raw, dtype=dt)])
+        eng.process()
+        eng.sync()
+        sd = eng.drain_soft(0)
+        if sd.size:
+            if o["soft"]:
+                fout.write(sd.tobytes())
+            elif o["M"] == 2:
+                fout.write((sd < 0).astype(np.uint8).tobytes())
+            else:
+                fout.write((sd > 0).astype(np.uint8).tobytes())
+            fout.flush()
+        if o["stats"] and sd.size:
+            frames_since += sd.size // eng.Nbits
+            a = np.abs(sd.astype(np.float64))
+            ebno = -6 + 20 * math.log10((1e-6 + a.mean()) / (1e-6 + a.std()))
+            snr_est = 0.5 * snr_est + 0.5 * ebno
+            if frames_since >= stats_every:
+                frames_since = 0
+                st = eng.stats(0)
+                d = {"secs": int(time.time()), "EbNodB": round(snr_est, 1), "ppm": int(st.ppm),
+                     "f1_est": round(st.f_est[0], 1), "f2_est": round(st.f_est[1], 1)}
+                if o["M"] == 4:
+                    d["f3_est"], d["f4_est"] = round(st.f_est[2], 1), round(st.f_est[3], 1)
+                d["eye_diagram"] = []
+                d["samp_fft"] = [round(float(v), 6) for v in st.samp_fft[:st.nfft]]
+                sys.stderr.write(json.dumps(d) + "\n")
+    fout.flush()
+    eng.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

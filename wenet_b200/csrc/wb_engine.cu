@@ -587,6 +587,36 @@ static void launch_fsk(wb_engine *e, const wb_fsk_args &a)
     else wb_fsk_kernel<M, TS, false><<<grid, e->spb * 32, e->fsk_smem, e->stream>>>(e->fp, a);
 }
 
+/* K2 -> K3 -> K4 -> carry over whatever soft decisions the rows hold (cursor[s].n_sd of them per stream) */
+static int launch_decode(wb_engine *e)
+{
+    const int n = e->cfg.n_streams;
+    if (e->cfg.framing != WB_FRAMING_NONE) {
+        wb_deframe_kernel<<<(n + 3) / 4, 128, 0, e->stream>>>(e->dp, e->d_state, e->d_cursor, e->d_sd, e->sd_stride,
+                                                               e->d_jobs, e->job_cap, n);
+        CU(cudaEventRecord(e->ev[2], e->stream));
+        size_t nslots = (size_t)n * e->job_cap;
+        wb_llr_stats_kernel<<<(unsigned)((nslots + 127) / 128), 128, 0, e->stream>>>(e->d_sd, e->sd_stride, e->d_jobs, e->d_c4,
+                                                                                    e->d_cursor, e->job_cap, n, e->cfg.framing, e->d_scramble);
+        CU(cudaEventRecord(e->ev[3], e->stream));
+        wb_ldpc_args la;
+        memset(&la, 0, sizeof(la));
+        la.sd = e->d_sd; la.sd_stride = e->sd_stride; la.jobs = e->d_jobs; la.c4 = e->d_c4; la.cur = e->d_cursor;
+        la.st = e->d_state; la.job_cap = e->job_cap; la.framing = e->cfg.framing; la.llr_in = nullptr;
+        la.cw = e->d_cw; la.llr_out = e->d_llr; la.max_iter = e->max_iter;
+        la.vedge = e->d_vedge; la.crc_tab = e->d_crc_tab; la.crc0 = e->crc0; la.scramble = e->d_scramble; la.lut = e->d_lut;
+        wb_ldpc_kernel<<<(unsigned)nslots, WB_LDPC_THREADS, sizeof(wb_ldpc_smem), e->stream>>>(la, 0);
+        CU(cudaEventRecord(e->ev[4], e->stream));
+        wb_carry_kernel<<<(n + 3) / 4, 128, 0, e->stream>>>(e->d_state, e->d_cursor, e->d_sd, e->sd_stride, n);
+        e->launches += 4;
+    } else {
+        CU(cudaEventRecord(e->ev[2], e->stream));
+        CU(cudaEventRecord(e->ev[3], e->stream));
+        CU(cudaEventRecord(e->ev[4], e->stream));
+    }
+    return WB_OK;
+}
+
 extern "C" int wb_process(wb_engine *e)
 {
     if (!e) return wb_fail(WB_EINVAL, "null engine");
@@ -614,29 +644,52 @@ extern "C" int wb_process(wb_engine *e)
     else launch_fsk<4, 10>(e, a);
     e->launches++;
     CU(cudaEventRecord(e->ev[1], e->stream));
-    if (e->cfg.framing != WB_FRAMING_NONE) {
-        wb_deframe_kernel<<<(n + 3) / 4, 128, 0, e->stream>>>(e->dp, e->d_state, e->d_cursor, e->d_sd, e->sd_stride,
-                                                               e->d_jobs, e->job_cap, n);
-        CU(cudaEventRecord(e->ev[2], e->stream));
-        size_t nslots = (size_t)n * e->job_cap;
-        wb_llr_stats_kernel<<<(unsigned)((nslots + 127) / 128), 128, 0, e->stream>>>(e->d_sd, e->sd_stride, e->d_jobs, e->d_c4,
-                                                                                    e->d_cursor, e->job_cap, n, e->cfg.framing, e->d_scramble);
-        CU(cudaEventRecord(e->ev[3], e->stream));
-        wb_ldpc_args la;
-        memset(&la, 0, sizeof(la));
-        la.sd = e->d_sd; la.sd_stride = e->sd_stride; la.jobs = e->d_jobs; la.c4 = e->d_c4; la.cur = e->d_cursor;
-        la.st = e->d_state; la.job_cap = e->job_cap; la.framing = e->cfg.framing; la.llr_in = nullptr;
-        la.cw = e->d_cw; la.llr_out = e->d_llr; la.max_iter = e->max_iter;
-        la.vedge = e->d_vedge; la.crc_tab = e->d_crc_tab; la.crc0 = e->crc0; la.scramble = e->d_scramble; la.lut = e->d_lut;
-        wb_ldpc_kernel<<<(unsigned)nslots, WB_LDPC_THREADS, sizeof(wb_ldpc_smem), e->stream>>>(la, 0);
-        CU(cudaEventRecord(e->ev[4], e->stream));
-        wb_carry_kernel<<<(n + 3) / 4, 128, 0, e->stream>>>(e->d_state, e->d_cursor, e->d_sd, e->sd_stride, n);
-        e->launches += 4;
-    } else {
-        CU(cudaEventRecord(e->ev[2], e->stream));
-        CU(cudaEventRecord(e->ev[3], e->stream));
-        CU(cudaEventRecord(e->ev[4], e->stream));
+    int rc2 = launch_decode(e);
+    if (rc2) return rc2;
+    CU(cudaGetLastError());
+    e->pending = true;
+    return WB_OK;
+}
+
+
+__global__ void wb_set_nsd_kernel(wb_cursor *cur, const unsigned long long *nsd, const wb_stream_state *st, int n)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    cur[s].n_sd = (unsigned)nsd[s];
+    cur[s].consumed = 0;
+    cur[s].n_jobs = 0;
+    cur[s].nin = st[s].nin;
+    /* in_fill (the parked IQ remainder) is left as it is */
+}
+
+/* the fread(&symbol) loop of drs232_ldpc.c:176 / wenet_ldpc.c:171 without a demodulator in front */
+extern "C" int wb_process_soft(wb_engine *e, const float *const *sd, const uint64_t *nsym)
+{
+    if (!e || !sd || !nsym) return wb_fail(WB_EINVAL, "null argument");
+    if (e->cfg.framing == WB_FRAMING_NONE) return wb_fail(WB_EINVAL, "engine was created without a framing");
+    if (e->resident_mode) return wb_fail(WB_EINVAL, "engine is in resident (wb_dev_set_fill) mode");
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    CU(cudaSetDevice(e->cfg.device));
+    const int n = e->cfg.n_streams;
+    std::vector<unsigned long long> cnt(n);
+    for (int s = 0; s < n; s++) {
+        if (nsym[s] > e->sd_cap) return wb_fail(WB_ERANGE, "stream %d: more than %u soft symbols per call", s, e->sd_cap);
+        if (nsym[s] && !sd[s]) return wb_fail(WB_EINVAL, "stream %d: null buffer", s);
+        cnt[s] = nsym[s];
     }
+    for (int s = 0; s < n; s++)
+        if (nsym[s])
+            CU(cudaMemcpyAsync(e->d_sd + (size_t)s * e->sd_stride + WB_CARRY_CAP, sd[s], sizeof(float) * nsym[s],
+                               cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->d_fill, cnt.data(), sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, e->stream));
+    wb_set_nsd_kernel<<<(n + 127) / 128, 128, 0, e->stream>>>(e->d_cursor, e->d_fill, e->d_state, n);
+    e->launches++;
+    CU(cudaEventRecord(e->ev[0], e->stream));
+    CU(cudaEventRecord(e->ev[1], e->stream));
+    rc = launch_decode(e);
+    if (rc) return rc;
     CU(cudaGetLastError());
     e->pending = true;
     return WB_OK;

@@ -67,6 +67,7 @@ ABI = [
     ("wb_feed", C.c_int, [_VP, _VP, _VP]),
     ("wb_feed_strided", C.c_int, [_VP, _VP, _U64, _U64]),
     ("wb_process", C.c_int, [_VP]),
+    ("wb_process_soft", C.c_int, [_VP, _VP, _VP]),
     ("wb_sync", C.c_int, [_VP]),
     ("wb_drain_packets", C.c_int, [_VP, C.c_int, _VP, _SZ, C.POINTER(_SZ)]),
     ("wb_drain_all_packets", C.c_int, [_VP, _VP, _SZ, C.POINTER(_SZ), C.POINTER(_U64)]),
@@ -228,6 +229,20 @@ class Engine:
 
     def process(self):
         self._check(self.lib.wb_process(self.h))
+
+    def process_soft(self, streams):
+        """Deframe + decode float32 soft symbols directly (what `drs232_ldpc` / `wenet_ldpc` read on stdin)."""
+        assert len(streams) == self.n_streams
+        keep, ptrs, ns = [], (C.c_void_p * self.n_streams)(), np.zeros(self.n_streams, dtype=np.uint64)
+        for s, a in enumerate(streams):
+            if a is None or len(a) == 0:
+                continue
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            keep.append(a)
+            ptrs[s] = a.ctypes.data
+            ns[s] = a.size
+        self._check(self.lib.wb_process_soft(self.h, ptrs, _ptr(ns)))
+        self._keep = keep
 
     def sync(self):
         self._check(self.lib.wb_sync(self.h))
