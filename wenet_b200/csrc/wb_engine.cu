@@ -465,6 +465,27 @@ extern "C" int wb_create(const wb_config *cfg, wb_engine **out)
         if (spb == 0) { wb_destroy(e); return wb_fail(WB_EINVAL, "FSK kernel does not fit shared memory"); }
         if (getenv("WB_FSK_SPB")) spb = std::max(1, std::min(max_spb, atoi(getenv("WB_FSK_SPB"))));
         e->spb = spb;
+        /* segments of the sequential mixer phase (see wb_fsk_kernel.cuh, B1): multiples of 8 steps, shrinking
+           geometrically by the cost ratio (bare recurrence step) / (recurrence + mix step) */
+        {
+            int W = std::min(spb, 4);
+            if (getenv("WB_FSK_B1W")) W = std::max(1, std::min(std::min(spb, WB_MAX_B1W), atoi(getenv("WB_FSK_B1W"))));
+            double r = getenv("WB_FSK_B1R") ? atof(getenv("WB_FSK_B1R")) : 0.75;
+            const int nsteps = e->fp.nsteps;
+            double tot = 0, wgt = 1;
+            for (int j = 0; j < W; j++) { tot += wgt; wgt *= r; }
+            int acc = 0; wgt = 1;
+            e->fp.b1_seg[0] = 0;
+            for (int j = 0; j < W; j++) {
+                int len = (int)(nsteps * wgt / tot / 8.0 + 0.5) * 8;
+                if (len < 8) len = 8;
+                acc += len; wgt *= r;
+                if (acc > nsteps || j == W - 1) acc = nsteps;
+                e->fp.b1_seg[j + 1] = acc;
+                if (acc == nsteps) { W = j + 1; break; }
+            }
+            e->fp.b1_w = W;
+        }
         e->fsk_smem = smem_for(spb);
         const bool cf32 = e->fp.in_fmt == WB_FMT_CF32;
         cudaError_t ce = cudaErrorInvalidValue;

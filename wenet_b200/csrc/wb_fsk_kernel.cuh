@@ -53,7 +53,7 @@
 #define WB_NST 1                     /* stash registers per lane: 2*Ts + Ts/2 <= 25 samples are carried over */
 #define WB_NEQ (WB_MAX_NDFT / 2 / 32)
 
-struct wb_fsk_sc {                 /* per-stream frame scalars in shared memory (88 bytes) */
+struct wb_fsk_sc {                 /* per-stream frame scalars in shared memory (96 bytes) */
     float2 phi_c[WB_MAXM];
     short pb[WB_MAXM];             /* estimator bins in force before this frame (fsk->f_est) */
     short nb[WB_MAXM];             /* bins estimated from this frame */
@@ -133,6 +133,25 @@ __device__ __forceinline__ float2 wb_ucmul(float2 a)
     return c;
 }
 
+/* cf32 frames go global -> shared memory with cp.async (no registers, no conversion) */
+__device__ __forceinline__ void wb_cp_async8(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void wb_cp_async_wait()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+/* FFT work buffer index: XOR bits 4..5 into both bit pairs below them.  The leaf stores (lanes differ in bits
+   2..5), the radix-4 level with m = 4 (lanes differ in bits 0..1 and 4..5) and the wider levels (lanes differ
+   in bits 0..3) all become bank-conflict free. */
+__device__ __forceinline__ int wb_fidx(int i)
+{
+    return i ^ (((i >> 4) & 3) * 5);
+}
+
 template <bool SWZ>
 __device__ __forceinline__ int wb_phys(int n)
 {
@@ -196,6 +215,23 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
         c.nin = p.N; c.flags = 0; c.nin_next = p.N; c.norm = 0.0f; c.ppm = 0.0f; c.rx_timing = 0.0f;
         c.low = c.high = 0; c.fract = 0.0f;
     }
+    /* cf32: start the copy of the frame at row position POS into X[nst ..] (zeros past the fill mark) */
+#define WB_FETCH_CF32(POS)                                                                              \
+    do {                                                                                                \
+        int sgv_ = sgc;                                                                                 \
+        asm volatile("" : "+r"(sgv_));                                                                  \
+        const float2 *row_ = reinterpret_cast<const float2 *>(WB_ROW_IN(sgv_));                         \
+        _Pragma("unroll")                                                                               \
+        for (int q_ = 0; q_ < NPRE; q_++) {                                                             \
+            const int n_ = lane + 32 * q_;                                                              \
+            if (n_ < p.nmax) {                                                                          \
+                if ((POS) + n_ < fill) wb_cp_async8(&X[nst + n_], row_ + (POS) + n_);                   \
+                else X[nst + n_] = make_float2(0.0f, 0.0f);                                             \
+            }                                                                                           \
+        }                                                                                               \
+    } while (0)
+    if (CF32 && have) WB_FETCH_CF32(pos);
+
     const float omt = __fsub_rn(1.0f, p.tc);
     const bool blocked = (p.step == 1);          /* P == Ts: the configuration every Wenet script uses */
 
@@ -225,9 +261,12 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                     lh[b][dd] = (lane + 32 * b < istr && dd < pp0 && n < nwin) ? __ldg(&p.hann[n]) : 0.0f;
                 }
             }
-            {
-                /* this frame's samples: L2 hits (prefetched into L2 a frame ago, see below), straight to shared
-                   memory.  The registers are only held for the round trip, at a point of low register pressure. */
+            if (CF32) {
+                /* this frame's samples were sent on their way (cp.async, global -> shared) at the end of the previous
+                   frame; wait for them */
+                wb_cp_async_wait();
+            } else {
+                /* converted formats go through registers: L2 hits (each frame is prefetched into L2 a frame ahead) */
                 int sgv = sgc;
                 asm volatile("" : "+r"(sgv));        /* opaque: recompute the row pointer here, do not carry it */
                 const unsigned char *in = WB_ROW_IN(sgv);
@@ -236,20 +275,23 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 for (int q = 0; q < NPRE; q++) {
                     const int n = lane + 32 * q;
                     pre_lo[q] = pre_hi[q] = 0u;
-                    if (n < p.nmax && pos + n < fill) wb_load_raw<CF32>(fmt, in, pos + n, pre_lo[q], pre_hi[q]);
-                }
-                /* next frame -> L2: one 128-byte line per lane, no registers held */
-                {
-                    const unsigned long long b0 = (unsigned long long)pos_next * p.in_bps;
-                    const unsigned long long off = (b0 & ~127ULL) + 128ULL * lane;
-                    if (off < b0 + (unsigned long long)p.nmax * p.in_bps && off < (unsigned long long)fill * p.in_bps)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(in + off));
+                    if (n < p.nmax && pos + n < fill) wb_load_raw<false>(fmt, in, pos + n, pre_lo[q], pre_hi[q]);
                 }
 #pragma unroll
                 for (int q = 0; q < NPRE; q++) {
                     const int n = lane + 32 * q;
-                    if (n < p.nmax) X[nst + n] = wb_convert<CF32>(fmt, pre_lo[q], pre_hi[q]);
+                    if (n < p.nmax) X[nst + n] = wb_convert<false>(fmt, pre_lo[q], pre_hi[q]);
                 }
+            }
+            {
+                /* the frame after this one -> L2: one 128-byte line per lane, no registers held */
+                int sgv = sgc;
+                asm volatile("" : "+r"(sgv));
+                const unsigned char *in = WB_ROW_IN(sgv);
+                const unsigned long long b0 = (unsigned long long)pos_next * p.in_bps;
+                const unsigned long long off = (b0 & ~127ULL) + 128ULL * lane;
+                if (off < b0 + (unsigned long long)p.nmax * p.in_bps && off < (unsigned long long)fill * p.in_bps)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(in + off));
             }
             __syncwarp();
             /* Estimator FFT (reference src/fsk.c:583-628, src/kiss_fft.c:238-306): decimation in time, the
@@ -277,35 +319,38 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                         const float2 s3 = make_float2(__fadd_rn(s0.x, s2.x), __fadd_rn(s0.y, s2.y));
                         const float2 s4 = make_float2(__fsub_rn(s0.x, s2.x), __fsub_rn(s0.y, s2.y));
                         /* (stream regions are only 8-byte aligned: float2 stores) */
-                        F[4 * t] = make_float2(__fadd_rn(aa.x, s3.x), __fadd_rn(aa.y, s3.y));
-                        F[4 * t + 1] = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));
-                        F[4 * t + 2] = make_float2(__fsub_rn(aa.x, s3.x), __fsub_rn(aa.y, s3.y));
-                        F[4 * t + 3] = make_float2(__fsub_rn(s5.x, s4.y), __fadd_rn(s5.y, s4.x));
+                        F[wb_fidx(4 * t)] = make_float2(__fadd_rn(aa.x, s3.x), __fadd_rn(aa.y, s3.y));
+                        F[wb_fidx(4 * t + 1)] = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));
+                        F[wb_fidx(4 * t + 2)] = make_float2(__fsub_rn(aa.x, s3.x), __fsub_rn(aa.y, s3.y));
+                        F[wb_fidx(4 * t + 3)] = make_float2(__fsub_rn(s5.x, s4.y), __fadd_rn(s5.y, s4.x));
                     } else {            /* reference src/kiss_fft.c:22-42 with m = 1 */
                         const float2 tt = wb_ucmul(f[1]);
-                        F[2 * t] = make_float2(__fadd_rn(f[0].x, tt.x), __fadd_rn(f[0].y, tt.y));
-                        F[2 * t + 1] = make_float2(__fsub_rn(f[0].x, tt.x), __fsub_rn(f[0].y, tt.y));
+                        F[wb_fidx(2 * t)] = make_float2(__fadd_rn(f[0].x, tt.x), __fadd_rn(f[0].y, tt.y));
+                        F[wb_fidx(2 * t + 1)] = make_float2(__fsub_rn(f[0].x, tt.x), __fsub_rn(f[0].y, tt.y));
                     }
                 }
             }
             __syncwarp();
             for (int L = 1; L < p.n_levels - 1; L++) {      /* middle levels: radix 4, twiddles from shared memory */
                 const int sh = p.lev_sh[L], mm = 1 << sh, fs = p.lev_fstride[L];
+                /* m <= 16 < 32: both butterflies of a lane (t = lane, lane + 32) share k and hence the twiddles */
+                const int k = lane & (mm - 1);
+                const float2 w1 = TW[k * fs], w2 = TW[2 * k * fs], w3 = TW[3 * k * fs];
                 for (int t = lane; t < (Ndft >> 2); t += 32) {
-                    const int k = t & (mm - 1);
                     const int base = ((t >> sh) << (sh + 2)) + k;
-                    const float2 f0 = F[base], f1 = F[base + mm], f2 = F[base + 2 * mm], f3 = F[base + 3 * mm];
-                    const float2 s0 = wb_cmul2(f1, TW[k * fs]);
-                    const float2 s1 = wb_cmul2(f2, TW[2 * k * fs]);
-                    const float2 s2 = wb_cmul2(f3, TW[3 * k * fs]);
+                    const int i0 = wb_fidx(base), i1 = wb_fidx(base + mm), i2 = wb_fidx(base + 2 * mm), i3 = wb_fidx(base + 3 * mm);
+                    const float2 f0 = F[i0], f1 = F[i1], f2 = F[i2], f3 = F[i3];
+                    const float2 s0 = wb_cmul2(f1, w1);
+                    const float2 s1 = wb_cmul2(f2, w2);
+                    const float2 s2 = wb_cmul2(f3, w3);
                     const float2 s5 = make_float2(__fsub_rn(f0.x, s1.x), __fsub_rn(f0.y, s1.y));
                     const float2 aa = make_float2(__fadd_rn(f0.x, s1.x), __fadd_rn(f0.y, s1.y));
                     const float2 s3 = make_float2(__fadd_rn(s0.x, s2.x), __fadd_rn(s0.y, s2.y));
                     const float2 s4 = make_float2(__fsub_rn(s0.x, s2.x), __fsub_rn(s0.y, s2.y));
-                    F[base + 2 * mm] = make_float2(__fsub_rn(aa.x, s3.x), __fsub_rn(aa.y, s3.y));
-                    F[base] = make_float2(__fadd_rn(aa.x, s3.x), __fadd_rn(aa.y, s3.y));
-                    F[base + mm] = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));
-                    F[base + 3 * mm] = make_float2(__fsub_rn(s5.x, s4.y), __fadd_rn(s5.y, s4.x));
+                    F[i2] = make_float2(__fsub_rn(aa.x, s3.x), __fsub_rn(aa.y, s3.y));
+                    F[i0] = make_float2(__fadd_rn(aa.x, s3.x), __fadd_rn(aa.y, s3.y));
+                    F[i1] = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));
+                    F[i3] = make_float2(__fsub_rn(s5.x, s4.y), __fadd_rn(s5.y, s4.x));
                 }
                 __syncwarp();
             }
@@ -320,7 +365,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 #define WB_TOP_BFLY(K, Q0, Q1)                                                                        \
                 do {                                                                                  \
                     const int k_ = (K);                                                               \
-                    const float2 f0 = F[k_], f1 = F[k_ + mtop], f2 = F[k_ + 2 * mtop], f3 = F[k_ + 3 * mtop]; \
+                    const float2 f0 = F[wb_fidx(k_)], f1 = F[wb_fidx(k_ + mtop)], f2 = F[wb_fidx(k_ + 2 * mtop)], f3 = F[wb_fidx(k_ + 3 * mtop)]; \
                     const float2 s0 = wb_cmul2(f1, TW[k_]);                                           \
                     const float2 s1 = wb_cmul2(f2, TW[2 * k_]);                                       \
                     const float2 s2 = wb_cmul2(f3, TW[3 * k_]);                                       \
@@ -385,8 +430,15 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
         }
         __syncthreads();
 
-        /* ================= B1: warp 0, lane = (tone, stream): oscillator + down-mix ================= */
-        if (warp == 0 && lane < M * spb) {
+        /* ========== B1: warps 0..W-1, lane = (tone, stream): oscillator + down-mix ========== */
+        /* The oscillator recurrence is sequential but does not depend on the samples, and a bare recurrence step
+           (6 flops) is several times cheaper than a recurrence + down-mix step.  So W warps all run the SAME 28
+           chains: warp j spins the bare recurrence up to its segment start b1_seg[j] and only then mixes its own
+           segment [b1_seg[j], b1_seg[j+1]) of the frame.  Segment lengths shrink geometrically so all warps
+           finish together; the redundant recurrences cost issue slots that are idle anyway and cut the
+           latency of the phase by about W/2.  (Segments are multiples of 8: the in-place swizzled stores of one
+           warp never touch samples another warp still has to read.) */
+        if (warp < p.b1_w && lane < M * spb) {
             const int m = lane / spb, s = lane - m * spb;
             wb_fsk_sc &c = sc[s];
             if (c.flags & 1) {
@@ -400,10 +452,16 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 const float2 dnew = __ldg(&p.dphi[nbn]);
                 const float2 *src = Xs + (nst - nold);
                 float2 *dst = (m == 0) ? Xs + (nst - nold) : Xs + p.xlen + (m - 1) * p.ylen;
-                const int nsteps = p.nsteps;
                 const int nold_lo = 2 * p.Ts - p.Ts / 2, nold_hi = 2 * p.Ts + p.Ts / 2;
-                /* batches of eight steps: all eight samples are loaded before the (in-place, swizzled) stores.
-                   cmult(sample, cconj(phi)) then phi *= dphi: reference src/fsk.c:794-798. */
+                const int seg0 = p.b1_seg[warp], seg1 = p.b1_seg[warp + 1];
+                /* old -> new samples: comp_normalize + this frame's tone, reference src/fsk.c:787-788 */
+#define WB_B1_SWITCH()                                                                                  \
+                do {                                                                                    \
+                    const float av = __fsqrt_rn(__fadd_rn(__fmul_rn(ph.x, ph.x), __fmul_rn(ph.y, ph.y))); \
+                    ph.x = __fdiv_rn(ph.x, av); ph.y = __fdiv_rn(ph.y, av);                             \
+                    d = dnew;                                                                           \
+                } while (0)
+                /* cmult(sample, cconj(phi)) then phi *= dphi: reference src/fsk.c:794-798 */
 #define WB_B1_STEP(J)                                                                                   \
                 do {                                                                                    \
                     const float ox_ = __fadd_rn(__fmul_rn(xv[J].x, ph.x), __fmul_rn(xv[J].y, ph.y));    \
@@ -411,21 +469,35 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                     xv[J] = make_float2(ox_, oy_);                                                      \
                     ph = wb_cmul2(ph, d);                                                               \
                 } while (0)
-                int n0 = 0;
-                /* (a) the batches that can contain the old -> new sample switch */
+                /* (0) bare recurrence up to the segment start */
+                int n = 0;
+                {
+                    const int na = min(seg0, nold_hi + 1);
 #pragma unroll 1
-                for (; n0 <= nold_hi; n0 += 8) {
+                    for (; n < na; n++) {
+                        if (n == nold) WB_B1_SWITCH();
+                        ph = wb_cmul2(ph, d);
+                    }
+#pragma unroll 1
+                    for (; n + 8 <= seg0; n += 8) {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) ph = wb_cmul2(ph, d);
+                    }
+#pragma unroll 1
+                    for (; n < seg0; n++) ph = wb_cmul2(ph, d);
+                }
+                /* batches of eight steps: all eight samples are loaded before the (in-place, swizzled) stores */
+                int n0 = seg0;
+                /* (a) the batches that can contain the switch */
+#pragma unroll 1
+                for (; n0 <= nold_hi && n0 + 8 <= seg1; n0 += 8) {
                     const int kb = SWZ ? ((n0 >> 4) & 7) : 0;
                     float2 xv[8];
 #pragma unroll
                     for (int j = 0; j < 8; j++) xv[j] = src[n0 + j];
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
-                        if (n0 + j == nold) {   /* comp_normalize + this frame's tone, reference src/fsk.c:787-788 */
-                            const float av = __fsqrt_rn(__fadd_rn(__fmul_rn(ph.x, ph.x), __fmul_rn(ph.y, ph.y)));
-                            ph.x = __fdiv_rn(ph.x, av); ph.y = __fdiv_rn(ph.y, av);
-                            d = dnew;
-                        }
+                        if (n0 + j == nold) WB_B1_SWITCH();
                         WB_B1_STEP(j);
                     }
 #pragma unroll
@@ -433,7 +505,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 }
                 /* (b) full batches, branch-free */
 #pragma unroll 1
-                for (; n0 + 8 <= nsteps; n0 += 8) {
+                for (; n0 + 8 <= seg1; n0 += 8) {
                     const int kb = SWZ ? ((n0 >> 4) & 7) : 0;
                     float2 xv[8];
 #pragma unroll
@@ -443,19 +515,22 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 #pragma unroll
                     for (int j = 0; j < 8; j++) dst[n0 + (j ^ kb)] = xv[j];
                 }
-                /* (c) the last, partial batch (its swizzle key is 0) */
+                /* (c) a partial batch only ends the last segment (its swizzle key is 0) */
                 {
                     const int kb = SWZ ? ((n0 >> 4) & 7) : 0;
 #pragma unroll 1
-                    for (int j = 0; n0 + j < nsteps; j++) {
+                    for (int j = 0; n0 + j < seg1; j++) {
                         float2 xv[1];
                         xv[0] = src[n0 + j];
+                        if (n0 + j == nold) WB_B1_SWITCH();
                         WB_B1_STEP(0);
                         dst[n0 + (j ^ kb)] = xv[0];
                     }
                 }
 #undef WB_B1_STEP
-                c.phi_c[m] = ph;
+#undef WB_B1_SWITCH
+                if (warp == p.b1_w - 1) c.phi_c[m] = ph;        /* the last segment ends the frame */
+                (void)nold_lo;
             }
         }
         __syncthreads();
@@ -552,34 +627,37 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
         __syncthreads();
 
         /* ================= B3: warp 0, lane = stream: fine-timing accumulation ================= */
-        if (warp == 0 && lane < spb) {
-            wb_fsk_sc &c = sc[lane];
-            if (c.flags & 1) {
-                const float *Es = reinterpret_cast<const float *>(
-                    reinterpret_cast<const float2 *>(regions + (size_t)lane * p.sreg) + p.xlen + p.blen);
-                float tcr = 0.0f, tci = 0.0f;
-                if (blocked) {
-                    /* fully unrolled: E positions and the oscillator table (kernel parameters = constant bank)
-                       are immediates; two dependent additions per output is all that is sequential */
+        if (warp == 0) {
+            /* all 32 lanes walk the loop (idle lanes shadow the last stream) so that the loop counter stays
+               warp-uniform and the oscillator table can be read from the constant bank at a uniform index */
+            const int s = min(lane, spb - 1);
+            wb_fsk_sc &c = sc[s];
+            const float *Es = reinterpret_cast<const float *>(
+                reinterpret_cast<const float2 *>(regions + (size_t)s * p.sreg) + p.xlen + p.blen);
+            float tcr = 0.0f, tci = 0.0f;
+            if (blocked) {
+                /* fully unrolled: E positions and the oscillator table (kernel parameters = constant bank) are
+                   immediates; two dependent additions per output are all that is sequential */
 #pragma unroll
-                    for (int i0 = 0; i0 < NBLK * TS; i0 += 14) {
-                        float ev[14];               /* 14 loads in flight, then 14 + 14 dependent additions */
+                for (int i0 = 0; i0 < NBLK * TS; i0 += 14) {
+                    float ev[14];
 #pragma unroll
-                        for (int j = 0; j < 14; j++) ev[j] = Es[((i0 + j) % TS) * NBLK + (i0 + j) / TS];
+                    for (int j = 0; j < 14; j++) ev[j] = Es[((i0 + j) % TS) * NBLK + (i0 + j) / TS];
 #pragma unroll
-                        for (int j = 0; j < 14; j++) {
-                            tcr = __fadd_rn(tcr, __fmul_rn(ev[j], p.pftc[i0 + j].x));          /* reference src/fsk.c:870 */
-                            tci = __fadd_rn(tci, __fmul_rn(ev[j], p.pftc[i0 + j].y));
-                        }
-                    }
-                } else {
-                    for (int i = 0; i < p.nint; i++) {
-                        const float e = Es[i];
-                        const float2 t2 = p.pftc[i];
-                        tcr = __fadd_rn(tcr, __fmul_rn(e, t2.x));
-                        tci = __fadd_rn(tci, __fmul_rn(e, t2.y));
+                    for (int j = 0; j < 14; j++) {
+                        tcr = __fadd_rn(tcr, __fmul_rn(ev[j], p.pftc[i0 + j].x));          /* reference src/fsk.c:870 */
+                        tci = __fadd_rn(tci, __fmul_rn(ev[j], p.pftc[i0 + j].y));
                     }
                 }
+            } else {
+                for (int i = 0; i < p.nint; i++) {
+                    const float e = Es[i];
+                    const float2 t2 = p.pftc[i];
+                    tcr = __fadd_rn(tcr, __fmul_rn(e, t2.x));
+                    tci = __fadd_rn(tci, __fmul_rn(e, t2.y));
+                }
+            }
+            if (lane < spb && (c.flags & 1)) {
                 const bool nan = isnan(tcr) || isnan(tci);     /* reference src/fsk.c:878-880 */
                 if (!nan) {
                     const float norm = (float)((double)wb_atan2f(tci, tcr) / 6.283185307179586);
@@ -646,6 +724,11 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             __syncwarp();
             /* old samples for the next frame */
             if (lane < nst) X[lane] = stash;
+            /* the integrator outputs in X are consumed: send the next frame's samples on their way */
+            if (CF32) {
+                const unsigned pn = pos_next;
+                WB_FETCH_CF32(pn);
+            }
             if (lane == 0) {
 #pragma unroll
                 for (int m = 0; m < M; m++) c.pb[m] = c.nb[m];              /* fsk->f_est = this frame's, :846 */

@@ -25,6 +25,7 @@
 #define WB_MAX_NSTASH (4 * WB_MAX_TS)
 #define WB_MAX_NIN 512                 /* N + Ts/2 must not exceed this */
 #define WB_MAX_LEVELS 8
+#define WB_MAX_B1W 14
 #define WB_MAX_NINT 496                /* (Nsym + 1) * P <= 49 * 10, rounded */
 #define WB_FRAME_SYMS 48               /* nsyms, reference src/fsk.c:134 */
 #define WB_FSK_THREADS 512             /* 16 stream-warps (2-FSK) / 8 stream-warps x 2 CTAs' worth (4-FSK: 256) */
@@ -48,6 +49,8 @@ struct wb_fsk_params {
     int n_levels;             /* FFT schedule, leaf first */
     int lev_p[WB_MAX_LEVELS], lev_m[WB_MAX_LEVELS], lev_fstride[WB_MAX_LEVELS], lev_sh[WB_MAX_LEVELS];
     int in_fmt, in_bps;       /* bytes per input sample */
+    int b1_w;                 /* warps sharing the sequential mixer phase, and their frame segments */
+    int b1_seg[WB_MAX_B1W + 1];
     int xlen, ylen, blen, sreg; /* smem geometry per stream: float2 of X, of one other-tone buffer, of all of them
                                   (>= Ndft: FFT work buffer); bytes per stream region (== 8 mod 16) */
     /* host-built constant tables (glibc cosf/sinf on the host = what the reference would use) */
