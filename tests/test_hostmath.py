@@ -59,7 +59,7 @@ def test_phi0_tables(hm, oracle_port):
     x = np.concatenate([rng.uniform(-1, 40, 500000), 2.0 ** rng.uniform(-20, 17, 500000),
                         [0.0, -0.0, np.nan, np.inf, -np.inf, 32768, 32767.99, 1e9, 10, 9.9999]]).astype(np.float32)
     ref = oracle_port.phi0(x)
-    for name in ("wbh_phi0", "wbh_phi0_compact"):
+    for name in ("wbh_phi0", "wbh_phi0_compact", "wbh_phi0_pairs"):
         got = _call(getattr(hm, name), x, out_dtype=np.float32)
         assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), name
     assert math.isclose(float(oracle_port.phi0(np.float32([0.5]))[0]), 1.5735153, rel_tol=1e-7)

@@ -79,7 +79,7 @@ struct wb_engine {
     uint16_t *d_crc_tab;
     unsigned crc0;
     uint8_t *d_scramble;
-    wb_phi0_compact *d_lut;
+    wb_phi0_pairs *d_lut;
     /* resident LDPC benchmark */
     float *d_bench_llr;
     uint8_t *d_bench_bits;
@@ -302,8 +302,8 @@ static int upload_tables(wb_engine *e)
     CU(cudaMemcpy(e->d_crc_tab, crc_tab.data(), sizeof(uint16_t) * 2048, cudaMemcpyHostToDevice));
     CU(cudaMalloc(&e->d_scramble, WB_SCRAMBLE_LEN));
     CU(cudaMemcpy(e->d_scramble, wb_scramble_neg, WB_SCRAMBLE_LEN, cudaMemcpyHostToDevice));
-    static wb_phi0_compact lut;
-    if (wb_phi0_build_compact(&lut) != 0) return wb_fail(WB_EINVAL, "phi0 table: two breakpoints in one bucket");
+    static wb_phi0_pairs lut;
+    if (wb_phi0_build_pairs(&lut) != 0) return wb_fail(WB_EINVAL, "phi0 table: two breakpoints in one bucket");
     CU(cudaMalloc(&e->d_lut, sizeof(lut)));
     CU(cudaMemcpy(e->d_lut, &lut, sizeof(lut), cudaMemcpyHostToDevice));
     return WB_OK;

@@ -220,14 +220,14 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     do {                                                                                                \
         int sgv_ = sgc;                                                                                 \
         asm volatile("" : "+r"(sgv_));                                                                  \
-        const float2 *row_ = reinterpret_cast<const float2 *>(WB_ROW_IN(sgv_));                         \
+        const float2 *row_ = reinterpret_cast<const float2 *>(WB_ROW_IN(sgv_)) + (POS);                 \
+        const int lim_ = (int)min((unsigned)p.nmax, fill > (POS) ? fill - (POS) : 0u);                  \
+        float2 *xd_ = X + nst;                                                                          \
         _Pragma("unroll")                                                                               \
         for (int q_ = 0; q_ < NPRE; q_++) {                                                             \
             const int n_ = lane + 32 * q_;                                                              \
-            if (n_ < p.nmax) {                                                                          \
-                if ((POS) + n_ < fill) wb_cp_async8(&X[nst + n_], row_ + (POS) + n_);                   \
-                else X[nst + n_] = make_float2(0.0f, 0.0f);                                             \
-            }                                                                                           \
+            if (n_ < lim_) wb_cp_async8(xd_ + n_, row_ + n_);                                           \
+            else if (n_ < p.nmax) xd_[n_] = make_float2(0.0f, 0.0f);                                    \
         }                                                                                               \
     } while (0)
     if (CF32 && have) WB_FETCH_CF32(pos);

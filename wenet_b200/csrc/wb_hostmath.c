@@ -54,3 +54,13 @@ void wbh_phi0_compact(const float *x, float *out, long n)
     wb_phi0_build_compact(&c);
     for (i = 0; i < n; i++) out[i] = wb_phi0_eval_compact(&c, x[i]);
 }
+
+long wbh_phi0_pairs(const float *x, float *out, long n)
+{
+    long i;
+    static wb_phi0_pairs t;
+    int rc = wb_phi0_build_pairs(&t);
+    if (rc) return rc;
+    for (i = 0; i < n; i++) out[i] = wb_phi0_eval_pairs(&t, x[i]);
+    return 0;
+}

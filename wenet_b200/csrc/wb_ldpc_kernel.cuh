@@ -50,7 +50,7 @@ struct wb_ldpc_args {
     const uint16_t *crc_tab;    /* [2048] CRC contribution of payload bit i */
     unsigned crc0;              /* CRC of 256 zero bytes */
     const uint8_t *scramble;    /* [1000] 1 = negate */
-    const wb_phi0_compact *lut;
+    const wb_phi0_pairs *lut;
 };
 
 /* symbol index inside a collected packet of codeword element c */
@@ -129,18 +129,19 @@ wb_llr_scale_kernel(const float *sd, const double *c4, float *llr, long long n_b
 
 struct wb_ldpc_smem {
     float msg[WB_LDPC_NMSG];            /* 28 896 B */
-    float llr[WB_NCODE];                /* 10 320 B */
-    wb_phi0_compact lut;                /*  2 832 B */
+    wb_phi0_pairs lut;                  /*  9 232 B */
     unsigned ballot[(WB_NCODE + 31) / 32 + 1];   /* hard decisions, bit l of word w = variable 32w + l */
     unsigned crc_part[4];
 };
 
-__device__ __forceinline__ float wb_phi0_s(const wb_phi0_compact &lut, float x)
+/* phi0 (reference src/phi0.c:13-218): two independent 8-byte loads and one compare, see wb_phi0.h */
+__device__ __forceinline__ float wb_phi0_s(const wb_phi0_pairs &lut, float x)
 {
     int b = ((int)__float_as_uint(x) >> 17) - (WB_PHI0_EXP0 << 6);
     b = max(0, min(b, WB_PHI0_NBUCKET));
-    const float4 en = *reinterpret_cast<const float4 *>(&lut.step[lut.sidx[b]]);
-    return (x < en.x) ? en.y : en.z;
+    const float2 p0 = *reinterpret_cast<const float2 *>(&lut.pt[b]);
+    const float2 p1 = *reinterpret_cast<const float2 *>(&lut.pt[b + 1]);
+    return (x < p0.x) ? p0.y : p1.y;
 }
 
 __device__ __forceinline__ float wb_signed(float mag, unsigned neg)
@@ -148,7 +149,7 @@ __device__ __forceinline__ float wb_signed(float mag, unsigned neg)
     return __uint_as_float(__float_as_uint(mag) | (neg << 31));   /* mag >= +0 */
 }
 
-__global__ void __launch_bounds__(WB_LDPC_THREADS)
+__global__ void __launch_bounds__(WB_LDPC_THREADS, 5)
 wb_ldpc_kernel(wb_ldpc_args a, long long n_direct)
 {
     extern __shared__ __align__(16) unsigned char wb_ldpc_raw[];
@@ -171,36 +172,50 @@ wb_ldpc_kernel(wb_ldpc_args a, long long n_direct)
     {
         const unsigned *src = reinterpret_cast<const unsigned *>(a.lut);
         unsigned *dst = reinterpret_cast<unsigned *>(&sm.lut);
-        for (int i = tid; i < (int)(sizeof(wb_phi0_compact) / 4); i += WB_LDPC_THREADS) dst[i] = src[i];
+        for (int i = tid; i < (int)(sizeof(wb_phi0_pairs) / 4); i += WB_LDPC_THREADS) dst[i] = src[i];
     }
-    /* LLRs: gather + scale (mode A) or load (mode B) */
+    /* LLRs: gather + scale (mode A) or load (mode B); thread tid owns variables tid + 288 r, r = 0..8, for the
+       whole decode, so their LLRs stay in registers */
+    float llr[9];
     if (direct) {
         const float *src = a.llr_in + slot * WB_NCODE;
-        for (int c = tid; c < WB_NCODE; c += WB_LDPC_THREADS) sm.llr[c] = src[c];
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+            const int c = tid + r * WB_LDPC_THREADS;
+            llr[r] = (c < WB_NCODE) ? src[c] : 0.0f;
+        }
     } else {
         const float *row = a.sd + (size_t)s * a.sd_stride + a.jobs[slot];
         const double c4 = a.c4[slot];
-        for (int c = tid; c < WB_NCODE; c += WB_LDPC_THREADS) {
-            float v = row[wb_cw_symbol(a.framing, c)];
-            if (a.framing == WB_FRAMING_V2 && a.scramble[c % WB_SCRAMBLE_LEN]) v = -v;
-            float l = wb_llr_scale(c4, v);
-            sm.llr[c] = l;
-            if (a.llr_out) a.llr_out[slot * WB_NCODE + c] = l;
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+            const int c = tid + r * WB_LDPC_THREADS;
+            llr[r] = 0.0f;
+            if (c < WB_NCODE) {
+                float v = row[wb_cw_symbol(a.framing, c)];
+                if (a.framing == WB_FRAMING_V2 && a.scramble[c % WB_SCRAMBLE_LEN]) v = -v;
+                llr[r] = wb_llr_scale(c4, v);
+                if (a.llr_out) a.llr_out[slot * WB_NCODE + c] = llr[r];
+            }
         }
     }
     __syncthreads();
 
     /* initial v->c messages, reference src/mpdecode_core.c:343-350 */
-    for (int i = tid; i < WB_NCODE; i += WB_LDPC_THREADS) {
-        float l = sm.llr[i];
-        float q = wb_signed(wb_phi0_s(sm.lut, fabsf(l)), (l < 0.0f) ? 1u : 0u);
-        if (i < WB_NDATA) {
-            ushort4 e = a.vedge[i];
-            sm.msg[e.x] = q; sm.msg[e.y] = q; sm.msg[e.z] = q;
-        } else {
-            int p = i - WB_NDATA;
-            sm.msg[13 * WB_NPAR + p] = q;
-            if (p < WB_NPAR - 1) sm.msg[12 * WB_NPAR + p + 1] = q;
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+        const int i = tid + r * WB_LDPC_THREADS;
+        if (i < WB_NCODE) {
+            const float l = llr[r];
+            const float q = wb_signed(wb_phi0_s(sm.lut, fabsf(l)), (l < 0.0f) ? 1u : 0u);
+            if (i < WB_NDATA) {
+                const ushort4 e = a.vedge[i];
+                sm.msg[e.x] = q; sm.msg[e.y] = q; sm.msg[e.z] = q;
+            } else {
+                const int p = i - WB_NDATA;
+                sm.msg[13 * WB_NPAR + p] = q;
+                if (p < WB_NPAR - 1) sm.msg[12 * WB_NPAR + p + 1] = q;
+            }
         }
     }
     __syncthreads();
@@ -238,14 +253,14 @@ wb_ldpc_kernel(wb_ldpc_args a, long long n_direct)
         }
         /* ---- variable-node pass, reference src/mpdecode_core.c:439-464 ---- */
         int nz = 0;
-#pragma unroll 1
+#pragma unroll
         for (int rnd = 0; rnd < 9; rnd++) {
-            int i = tid + rnd * WB_LDPC_THREADS;
+            const int i = tid + rnd * WB_LDPC_THREADS;
             bool bit = false;
             if (i < WB_NDATA) {
                 ushort4 e = a.vedge[i];
                 float r0 = sm.msg[e.x], r1 = sm.msg[e.y], r2 = sm.msg[e.z];
-                float Qi = sm.llr[i];
+                float Qi = llr[rnd];
                 Qi = Qi + r0; Qi = Qi + r1; Qi = Qi + r2;
                 bit = Qi < 0.0f;
                 float t0 = Qi - r0, t1 = Qi - r1, t2 = Qi - r2;
@@ -258,7 +273,7 @@ wb_ldpc_kernel(wb_ldpc_args a, long long n_direct)
                 int e0 = 13 * WB_NPAR + p, e1 = 12 * WB_NPAR + p + 1;
                 bool two = p < WB_NPAR - 1;
                 float r0 = sm.msg[e0], r1 = two ? sm.msg[e1] : 0.0f;
-                float Qi = sm.llr[i];
+                float Qi = llr[rnd];
                 Qi = Qi + r0;
                 if (two) Qi = Qi + r1;
                 bit = Qi < 0.0f;

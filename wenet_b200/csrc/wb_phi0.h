@@ -134,4 +134,38 @@ WB_HD float wb_phi0_eval_compact(const wb_phi0_compact *c, float x)
     return (x < en.thr) ? en.vlo : en.vhi;
 }
 
+
+/* ---- pair form: one level of independent loads ------------------------------
+ * pt[b] = {threshold inside bucket b (or +inf), value at the start of bucket b}; a bucket holds at most one
+ * breakpoint, after which the value is the one the next bucket starts with:
+ *     phi0(x) = (x < pt[b].thr) ? pt[b].val : pt[b+1].val
+ * Entry NENTRY (one past the clamp bucket) = {+inf, 10}: x >= 32768 and NaN (cvttss2si overflow quirk). */
+typedef struct { float thr, val; } wb_phi0_pair;
+#define WB_PHI0_NPAIR (WB_PHI0_NENTRY + 1)
+typedef struct { wb_phi0_pair pt[WB_PHI0_NPAIR]; } wb_phi0_pairs;     /* 1154 x 8 B */
+
+static inline int wb_phi0_build_pairs(wb_phi0_pairs *t)
+{
+    wb_phi0_lut full;
+    int b;
+    if (wb_phi0_build(&full) != 0) return -1;
+    for (b = 0; b < WB_PHI0_NENTRY; b++) {
+        t->pt[b].val = full.e[b].vlo;
+        t->pt[b].thr = (full.e[b].vlo != full.e[b].vhi || b == WB_PHI0_NBUCKET) ? full.e[b].thr : wb_u2f(0x7f800000u);
+    }
+    t->pt[WB_PHI0_NENTRY].thr = wb_u2f(0x7f800000u);
+    t->pt[WB_PHI0_NENTRY].val = 10.0f;
+    /* consistency: the value after a breakpoint must be what the next bucket starts with */
+    for (b = 0; b < WB_PHI0_NBUCKET; b++)
+        if (full.e[b].vlo != full.e[b].vhi && full.e[b].vhi != full.e[b + 1].vlo) return -2;
+    return 0;
+}
+
+WB_HD float wb_phi0_eval_pairs(const wb_phi0_pairs *t, float x)
+{
+    const int b = wb_phi0_bucket(x);
+    const wb_phi0_pair p0 = t->pt[b], p1 = t->pt[b + 1];
+    return (x < p0.thr) ? p0.val : p1.val;
+}
+
 #endif /* WB_PHI0_H */
