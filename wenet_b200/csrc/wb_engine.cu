@@ -200,7 +200,9 @@ static int build_fsk_params(const wb_config *cfg, wb_fsk_params *fp)
     fp->xlen = (fp->nst + fp->nmax + 1) & ~1;
     fp->ylen = (fp->nsteps + 1) & ~1;
     fp->blen = std::max((M - 1) * fp->ylen, Ndft);
-    int bytes = (fp->xlen + fp->blen) * 8 + ((fp->nint * 4 + 7) & ~7);
+    /* E: nint floats (general P) or two half-frames of re/im terms, (Nsym/2 + 1) blocks of P each */
+    int efl = std::max(fp->nint, 2 * ((fp->Nsym + 2) / 2) * fp->P);
+    int bytes = (fp->xlen + fp->blen) * 8 + ((efl * 4 + 7) & ~7);
     fp->sreg = (bytes & ~15) + 8;                              /* == 8 (mod 16): lanes of warp 0 hit distinct banks */
     if (fp->sreg < bytes) fp->sreg += 16;
     return WB_OK;

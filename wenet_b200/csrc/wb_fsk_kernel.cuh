@@ -53,14 +53,17 @@
 #define WB_NST 1                     /* stash registers per lane: 2*Ts + Ts/2 <= 25 samples are carried over */
 #define WB_NEQ (WB_MAX_NDFT / 2 / 32)
 
-struct wb_fsk_sc {                 /* per-stream frame scalars in shared memory (96 bytes) */
+struct wb_fsk_sc {                 /* per-stream frame scalars in shared memory (80 bytes) */
     float2 phi_c[WB_MAXM];
     short pb[WB_MAXM];             /* estimator bins in force before this frame (fsk->f_est) */
     short nb[WB_MAXM];             /* bins estimated from this frame */
-    int nin, flags, nin_next;      /* flags: bit 0 = active this frame, bit 1 = NaN guard tripped */
-    int low, high;
+    short nin, nin_next;
+    short low, high;
+    int flags;                     /* bit 0 = active this frame, bit 1 = NaN guard tripped */
     float fract, norm, ppm, rx_timing;
+    int pad;
 };
+static_assert(sizeof(wb_fsk_sc) == 80, "shared-memory budget of wb_fsk_kernel");
 
 struct wb_fsk_args {
     wb_stream_state *state;
@@ -167,6 +170,9 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     constexpr int NPRE = (TS * WB_FRAME_SYMS + TS / 2 + 31) / 32;     /* lanes x NPRE >= nmax */
     constexpr bool SWZ = (TS == 8);
     constexpr int NBLK = WB_FRAME_SYMS + 1;                           /* integrator outputs come in 49 blocks of P */
+    constexpr int B3H = NBLK / 2;                                     /* blocks in the first pass of B3 (24) */
+    constexpr int B3E = (NBLK - B3H) * TS;                            /* floats per component half in E (200) */
+    constexpr bool B3SWZ = (TS == 8);                                 /* 4 pairs per block: XOR-swizzle the pair index */
     extern __shared__ __align__(16) unsigned char wb_fsk_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int spb = a.spb;
@@ -207,12 +213,12 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             wb_fsk_sc &c = sc[warp];
             for (int m = 0; m < M; m++) { c.phi_c[m] = st->phi_c[m]; c.pb[m] = (short)st->fbin[m]; c.nb[m] = 0; }
             c.norm = st->norm_rx_timing; c.ppm = st->ppm; c.rx_timing = st->rx_timing;
-            c.nin = nin; c.nin_next = nin; c.flags = 0; c.low = c.high = 0; c.fract = 0.0f;
+            c.nin = (short)nin; c.nin_next = (short)nin; c.flags = 0; c.low = c.high = 0; c.fract = 0.0f;
         }
     } else if (lane == 0) {
         wb_fsk_sc &c = sc[warp];
         for (int m = 0; m < M; m++) { c.phi_c[m] = make_float2(1.0f, 0.0f); c.pb[m] = 0; c.nb[m] = 0; }
-        c.nin = p.N; c.flags = 0; c.nin_next = p.N; c.norm = 0.0f; c.ppm = 0.0f; c.rx_timing = 0.0f;
+        c.nin = (short)p.N; c.flags = 0; c.nin_next = (short)p.N; c.norm = 0.0f; c.ppm = 0.0f; c.rx_timing = 0.0f;
         c.low = c.high = 0; c.fract = 0.0f;
     }
     /* cf32: start the copy of the frame at row position POS into X[nst ..] (zeros past the fill mark) */
@@ -423,7 +429,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 const bool first = c.pb[0] == 0;         /* fsk->f_est[0] < 1, reference src/fsk.c:729 */
 #pragma unroll
                 for (int m = 0; m < M; m++) { c.nb[m] = (short)freqi[m]; if (first) c.pb[m] = (short)freqi[m]; }
-                c.nin = nin; c.flags = 1;
+                c.nin = (short)nin; c.flags = 1;
             }
         } else if (lane == 0) {
             sc[warp].flags = 0;
@@ -539,14 +545,24 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
         /* f_int[m][i] = sum of the Ts ring-buffer slots after mixer step i*step + Ts - 1, added in slot order
            (reference src/fsk.c:835-838): slot j holds the product of the step n in [i*step, i*step + Ts) with
            n mod Ts == j.  In place: output i overwrites product i. */
+        /* terms of the fine-timing sum of the one block per lane that belongs to the second pass of B3 */
+        float dre[TS], dim[TS];
+        int dblk = -1;
+#pragma unroll
+        for (int t = 0; t < TS; t++) { dre[t] = 0.0f; dim[t] = 0.0f; }
         if (active && blocked) {
             /* step = 1: lane u owns outputs Ts*u .. Ts*u + Ts - 1.  It needs products Ts*u .. Ts*u + 2Ts - 2; output
                Ts*u + t adds, in slot order, the first t products of block u+1 (a running prefix shared by all t)
-               and then products t .. Ts-1 of block u.  e goes to E[t * 49 + u] (conflict-free here, and B3 knows
-               the positions at compile time). */
-            for (int u0 = 0; u0 < NBLK; u0 += 32) {
-                const int u = u0 + lane;
+               and then products t .. Ts-1 of block u.  The terms of the fine-timing sum, e * phi_ft (reference
+               src/fsk.c:870), are formed here in parallel and handed to B3 through E in two halves. */
+            static_assert(NBLK <= 64, "two rounds of 32 lanes cover the blocks");
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                const int u = 32 * rr + lane;
                 const bool valid = u < NBLK;
+                float e[TS];
+#pragma unroll
+                for (int t = 0; t < TS; t++) e[t] = 0.0f;
 #pragma unroll
                 for (int m = 0; m < M; m++) {
                     float2 *P = (m == 0) ? X + xo : Y + (m - 1) * p.ylen;
@@ -577,12 +593,39 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                                 if (o >= o0) { sr = __fadd_rn(sr, vv[o].x); si = __fadd_rn(si, vv[o].y); }
                             P[TS * u + (t ^ k0)] = make_float2(sr, si);
                             const float pw = __fadd_rn(__fmul_rn(sr, sr), __fmul_rn(si, si));
-                            float *ep = E + t * NBLK + u;
-                            if (m == 0) *ep = pw;
-                            else *ep = __fadd_rn(*ep, pw);               /* reference src/fsk.c:864-867 */
+                            e[t] = (m == 0) ? pw : __fadd_rn(e[t], pw);      /* reference src/fsk.c:864-867 */
                         }
                     }
                     __syncwarp();
+                }
+                if (valid) {
+                    /* blocks 0..B3H-1 feed the first pass of B3 (E = [re terms | im terms], in output order);
+                       a lane owns at most one later block (lanes 24..31 in round 0, lanes 0..16 in round 1):
+                       its terms wait in registers */
+                    /* E = [re terms | im terms], B3E floats each, a block's TS terms stored as float2 pairs at pair
+                       index (p ^ key), key = (block >> 2) & 3: conflict-free stores here, aligned 8-byte loads in B3 */
+                    const float2 *pf = p.pft + u * TS;
+                    float tr[TS], ti[TS];
+#pragma unroll
+                    for (int t = 0; t < TS; t++) {
+                        const float2 w = __ldg(pf + t);
+                        tr[t] = __fmul_rn(e[t], w.x);                              /* reference src/fsk.c:870 */
+                        ti[t] = __fmul_rn(e[t], w.y);
+                    }
+                    if (u < B3H) {
+                        float2 *er = reinterpret_cast<float2 *>(E) + u * (TS / 2);
+                        float2 *ei = reinterpret_cast<float2 *>(E + B3E) + u * (TS / 2);
+                        const int key = B3SWZ ? ((u >> 2) & 3) : 0;
+#pragma unroll
+                        for (int q = 0; q < TS / 2; q++) {
+                            er[q ^ key] = make_float2(tr[2 * q], tr[2 * q + 1]);
+                            ei[q ^ key] = make_float2(ti[2 * q], ti[2 * q + 1]);
+                        }
+                    } else {
+                        dblk = u - B3H;
+#pragma unroll
+                        for (int t = 0; t < TS; t++) { dre[t] = tr[t]; dim[t] = ti[t]; }
+                    }
                 }
             }
         } else if (active) {
@@ -626,38 +669,58 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
         }
         __syncthreads();
 
-        /* ================= B3: warp 0, lane = stream: fine-timing accumulation ================= */
-        if (warp == 0) {
-            /* all 32 lanes walk the loop (idle lanes shadow the last stream) so that the loop counter stays
-               warp-uniform and the oscillator table can be read from the constant bank at a uniform index */
-            const int s = min(lane, spb - 1);
-            wb_fsk_sc &c = sc[s];
-            const float *Es = reinterpret_cast<const float *>(
-                reinterpret_cast<const float2 *>(regions + (size_t)s * p.sreg) + p.xlen + p.blen);
-            float tcr = 0.0f, tci = 0.0f;
-            if (blocked) {
-                /* fully unrolled: E positions and the oscillator table (kernel parameters = constant bank) are
-                   immediates; two dependent additions per output are all that is sequential */
+        /* ============ B3: warp 0, lane = (re/im, stream): fine-timing accumulation ============ */
+        /* t_c = sum_i e_i * phi_ft[i] is strictly sequential (reference src/fsk.c:858-873).  With the terms already
+           formed by B2, what is left per output is one load and one dependent addition per component, and the two
+           components run in different lanes.  E holds half a frame of terms at a time ([re | im], output order):
+           pass 1 = blocks 0..23, then the stream warps drop in blocks 24..48, pass 2. */
+        float tacc = 0.0f;
+        const int b3c = (lane < spb) ? 0 : 1, b3s = min(lane - b3c * spb, spb - 1);
+        const bool b3_lane = (warp == 0) && (lane < 2 * spb) && (sc[b3s].flags & 1);
+        const float *Es = reinterpret_cast<const float *>(
+            reinterpret_cast<const float2 *>(regions + (size_t)b3s * p.sreg) + p.xlen + p.blen);
+        if (blocked) {
+#define WB_B3_PASS(NB)                                                                                  \
+            do {                                                                                        \
+                if (b3_lane) {                                                                          \
+                    const float2 *q_ = reinterpret_cast<const float2 *>(Es + b3c * B3E);                \
+                    _Pragma("unroll 1")                                                                 \
+                    for (int u = 0; u < (NB); u++) {                                                    \
+                        const int key_ = B3SWZ ? ((u >> 2) & 3) : 0;                                    \
+                        float2 ev[TS / 2];                                                              \
+                        _Pragma("unroll")                                                               \
+                        for (int t = 0; t < TS / 2; t++) ev[t] = q_[u * (TS / 2) + (t ^ key_)];         \
+                        _Pragma("unroll")                                                               \
+                        for (int t = 0; t < TS / 2; t++) { tacc = __fadd_rn(tacc, ev[t].x); tacc = __fadd_rn(tacc, ev[t].y); } \
+                    }                                                                                   \
+                }                                                                                       \
+            } while (0)
+            WB_B3_PASS(B3H);
+            __syncthreads();
+            if (active && dblk >= 0) {
+                float2 *er = reinterpret_cast<float2 *>(E) + dblk * (TS / 2);
+                float2 *ei = reinterpret_cast<float2 *>(E + B3E) + dblk * (TS / 2);
+                const int key = B3SWZ ? ((dblk >> 2) & 3) : 0;
 #pragma unroll
-                for (int i0 = 0; i0 < NBLK * TS; i0 += 14) {
-                    float ev[14];
-#pragma unroll
-                    for (int j = 0; j < 14; j++) ev[j] = Es[((i0 + j) % TS) * NBLK + (i0 + j) / TS];
-#pragma unroll
-                    for (int j = 0; j < 14; j++) {
-                        tcr = __fadd_rn(tcr, __fmul_rn(ev[j], p.pftc[i0 + j].x));          /* reference src/fsk.c:870 */
-                        tci = __fadd_rn(tci, __fmul_rn(ev[j], p.pftc[i0 + j].y));
-                    }
-                }
-            } else {
-                for (int i = 0; i < p.nint; i++) {
-                    const float e = Es[i];
-                    const float2 t2 = p.pftc[i];
-                    tcr = __fadd_rn(tcr, __fmul_rn(e, t2.x));
-                    tci = __fadd_rn(tci, __fmul_rn(e, t2.y));
+                for (int q = 0; q < TS / 2; q++) {
+                    er[q ^ key] = make_float2(dre[2 * q], dre[2 * q + 1]);
+                    ei[q ^ key] = make_float2(dim[2 * q], dim[2 * q + 1]);
                 }
             }
-            if (lane < spb && (c.flags & 1)) {
+            __syncthreads();
+            WB_B3_PASS(NBLK - B3H);
+#undef WB_B3_PASS
+        } else if (b3_lane) {
+            for (int i = 0; i < p.nint; i++) {
+                const float2 t2 = p.pftc[i];
+                tacc = __fadd_rn(tacc, __fmul_rn(Es[i], b3c ? t2.y : t2.x));          /* reference src/fsk.c:870 */
+            }
+        }
+        if (warp == 0) {
+            const float tcr = __shfl_sync(0xffffffffu, tacc, b3s);
+            const float tci = __shfl_sync(0xffffffffu, tacc, min(spb + b3s, 31));
+            if (b3_lane && b3c == 0) {
+                wb_fsk_sc &c = sc[b3s];
                 const bool nan = isnan(tcr) || isnan(tci);     /* reference src/fsk.c:878-880 */
                 if (!nan) {
                     const float norm = (float)((double)wb_atan2f(tci, tcr) / 6.283185307179586);
@@ -668,13 +731,13 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                         const float appm = (float)(1e6 * (double)dn / (double)(float)p.Nsym);
                         c.ppm = (float)(.9 * (double)c.ppm + .1 * (double)appm);
                     }
-                    if ((double)norm > 0.25) c.nin_next = p.N + p.Ts / 2;
-                    else if ((double)norm < -0.25) c.nin_next = p.N - p.Ts / 2;
-                    else c.nin_next = p.N;
+                    if ((double)norm > 0.25) c.nin_next = (short)(p.N + p.Ts / 2);
+                    else if ((double)norm < -0.25) c.nin_next = (short)(p.N - p.Ts / 2);
+                    else c.nin_next = (short)p.N;
                     const int low = (int)floorf(rx_timing);
-                    c.low = low;
+                    c.low = (short)low;
                     c.fract = __fsub_rn(rx_timing, (float)low);
-                    c.high = (int)ceilf(rx_timing);
+                    c.high = (short)(int)ceilf(rx_timing);
                     c.rx_timing = rx_timing;
                 } else {
                     c.flags = 3;
