@@ -684,14 +684,20 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             do {                                                                                        \
                 if (b3_lane) {                                                                          \
                     const float2 *q_ = reinterpret_cast<const float2 *>(Es + b3c * B3E);                \
+                    float2 ev[TS / 2], en[TS / 2];                                                      \
+                    _Pragma("unroll")                                                                   \
+                    for (int t = 0; t < TS / 2; t++) ev[t] = q_[t];            /* block 0: key 0 */     \
                     _Pragma("unroll 1")                                                                 \
                     for (int u = 0; u < (NB); u++) {                                                    \
-                        const int key_ = B3SWZ ? ((u >> 2) & 3) : 0;                                    \
-                        float2 ev[TS / 2];                                                              \
+                        /* the next block's terms are on their way while this block's additions run */ \
+                        const int un_ = (u + 1 < (NB)) ? u + 1 : u;                                     \
+                        const int key_ = B3SWZ ? ((un_ >> 2) & 3) : 0;                                  \
                         _Pragma("unroll")                                                               \
-                        for (int t = 0; t < TS / 2; t++) ev[t] = q_[u * (TS / 2) + (t ^ key_)];         \
+                        for (int t = 0; t < TS / 2; t++) en[t] = q_[un_ * (TS / 2) + (t ^ key_)];       \
                         _Pragma("unroll")                                                               \
                         for (int t = 0; t < TS / 2; t++) { tacc = __fadd_rn(tacc, ev[t].x); tacc = __fadd_rn(tacc, ev[t].y); } \
+                        _Pragma("unroll")                                                               \
+                        for (int t = 0; t < TS / 2; t++) ev[t] = en[t];                                 \
                     }                                                                                   \
                 }                                                                                       \
             } while (0)
@@ -782,7 +788,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 /* NaN guard: the reference returns before writing, so the caller's buffer still holds
                    the previous frame's values (zeros before the first frame) */
                 for (int i = lane; i < p.Nbits; i += 32)
-                    out[i] = (n_out >= (unsigned)p.Nbits) ? out[i - p.Nbits] : 0.0f;
+                    out[i] = (n_out >= (unsigned)p.Nbits) ? out[i - p.Nbits] : st->sd_last[i];
             }
             __syncwarp();
             /* old samples for the next frame */
@@ -817,6 +823,10 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
         for (int q = 0; q < WB_NEQ; q++)
             if (lane + 32 * q < nh) st->fft_est[lane + 32 * q] = est[q];
         if (lane < nst) st->samp_old[lane] = X[lane];
+        if (n_out >= (unsigned)p.Nbits) {
+            const float *lastf = WB_ROW_SD(sg) + n_out - p.Nbits;
+            for (int i = lane; i < p.Nbits; i += 32) st->sd_last[i] = lastf[i];
+        }
         const unsigned char *in = WB_ROW_IN(sg);
         const unsigned long long rem = fill - pos;
         const unsigned long long dstpos = (unsigned long long)a.headroom - rem;   /* remainder ends at the headroom mark */

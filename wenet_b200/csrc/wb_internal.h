@@ -75,6 +75,7 @@ struct wb_stream_state {
     unsigned long long frames;
     float  fft_est[WB_MAX_NDFT / 2];
     float2 samp_old[WB_MAX_NSTASH];
+    float  sd_last[2 * WB_FRAME_SYMS];   /* last frame's soft decisions: re-emitted when the NaN guard trips, src/fsk.c:878 */
     /* deframer, reference locals of main() src/drs232_ldpc.c:106-118 */
     unsigned long long window;  /* bit_buffer, newest bit = bit 0 */
     int    collecting, ind;
