@@ -155,6 +155,21 @@ __device__ __forceinline__ int wb_fidx(int i)
     return i ^ (((i >> 4) & 3) * 5);
 }
 
+/* small constant tables in global memory (fine-timing oscillator, Hann window, leaf order): keep their lines in L1
+   against the streaming local-memory / sample traffic */
+__device__ __forceinline__ float2 wb_ldg_keep2(const float2 *p)
+{
+    float2 v;
+    asm("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float wb_ldg_keep(const float *p)
+{
+    float v;
+    asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 template <bool SWZ>
 __device__ __forceinline__ int wb_phys(int n)
 {
@@ -264,7 +279,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 #pragma unroll
                 for (int dd = 0; dd < 4; dd++) {
                     const int n = lbase[b] + dd * istr;
-                    lh[b][dd] = (lane + 32 * b < istr && dd < pp0 && n < nwin) ? __ldg(&p.hann[n]) : 0.0f;
+                    lh[b][dd] = (lane + 32 * b < istr && dd < pp0 && n < nwin) ? wb_ldg_keep(&p.hann[n]) : 0.0f;
                 }
             }
             if (CF32) {
@@ -608,7 +623,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                     float tr[TS], ti[TS];
 #pragma unroll
                     for (int t = 0; t < TS; t++) {
-                        const float2 w = __ldg(pf + t);
+                        const float2 w = wb_ldg_keep2(pf + t);
                         tr[t] = __fmul_rn(e[t], w.x);                              /* reference src/fsk.c:870 */
                         ti[t] = __fmul_rn(e[t], w.y);
                     }
