@@ -339,8 +339,19 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     fsk_gbs = ALG_BYTES_PER_SAMPLE_FSK * samples_step / (kms[0] * 1e-3) / 1e9 if kms[0] > 0 else 0.0
+    # DRAM traffic of the dominant kernel per launch: one `ncu --set full` capture of this same workload
+    # (profiles/r01_traffic.json says how it was taken); null for any other workload
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            tj = json.load(fh)
+        w = tj["wb_fsk_kernel"]["workload"]
+        if w["streams"] == n and w["chunk_samples"] == chunk and w["in_fmt"] == "cf32":
+            traffic = tj["wb_fsk_kernel"]["dram_bytes_read"] + tj["wb_fsk_kernel"]["dram_bytes_write"]
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": "wb_fsk_kernel", "achieved": round(fsk_gbs, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(fsk_gbs / peak, 4), "traffic": None,
+                "frac": round(fsk_gbs / peak, 4), "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "kernel_ms": {"fsk": round(float(kms[0]), 3), "deframe": round(float(kms[1]), 3),
                               "llr_stats": round(float(kms[2]), 3), "ldpc": round(float(kms[3]), 3)},
