@@ -375,6 +375,7 @@ extern "C" int wb_create(const wb_config *cfg, wb_engine **out)
     if (cfg->framing < WB_FRAMING_NONE || cfg->framing > WB_FRAMING_V2) return wb_fail(WB_EINVAL, "unknown framing");
     if (cfg->framing != WB_FRAMING_NONE && cfg->M != 2) return wb_fail(WB_EINVAL, "framing needs 2-FSK (the reference has no 4-FSK deframer)");
     if (cfg->chunk_samples < 1024) return wb_fail(WB_EINVAL, "chunk_samples too small");
+    if (cfg->chunk_samples > 0xF0000000ull) return wb_fail(WB_EINVAL, "chunk_samples too large (row positions are 32-bit)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
         return wb_fail(WB_ENODEV, "no CUDA device visible: libwenet_b200 has no CPU fallback");
