@@ -322,3 +322,28 @@ def test_golden_vectors_through_the_engine(eng_mod):
     e.sync()
     assert np.array_equal(e.drain_soft(0).view(np.uint32), z4["sd"].view(np.uint32))
     e.close()
+
+
+def test_stats_surface(eng_mod, oracle_port):
+    """wb_get_stats (the stderr JSON fields of src/fsk_demod.c:345-401): f_est, ppm, timing exact; snr_est (EbNodB) is the
+    reference's 0.5/0.5 IIR replayed over the last 32 frames; eye diagram where the reference's own indexing is defined"""
+    cfg = siggen.V1
+    raw, _ = siggen.make_stream(90, n_packets=2, ebno_db=11.0, fmt="cf32", clock_ppm=800.0)
+    f = oracle_port.fsk(cfg["Fs"], cfg["Rs"])
+    sd_o, log_o, _ = f.run(raw, "cf32")
+    so = f.state()
+    e = eng_mod.Engine(1, in_fmt="cf32", framing="none", chunk_samples=raw.size // 2 + 1024, stats=True)
+    e.feed([raw]); e.process(); e.sync()
+    st = e.stats(0)
+    assert st.f_est[0] == so[8] and st.f_est[1] == so[9]
+    assert np.float32(st.ppm) == so[13] and np.float32(st.norm_rx_timing) == so[12] and np.float32(st.rx_timing) == so[16]
+    assert np.float32(st.foff) == so[17]
+    assert abs(st.EbNodB - so[15]) < 1e-4, (st.EbNodB, so[15])
+    assert st.frames == len(log_o) and st.nfft == 128
+    assert np.array_equal(np.array(st.samp_fft[:128], dtype=np.float32).view(np.uint32), f.fft_est().view(np.uint32))
+    eye_o = f.eye()
+    eye_g = np.array([[st.rx_eye[i][j] for j in range(st.neyesamp)] for i in range(st.neyetr)], dtype=np.float32)
+    assert eye_g.shape == eye_o.shape == (8, 16)
+    if so[16] >= -1.0:            # high_sample + 1 >= 0: the reference's indices stay inside f_int
+        assert np.allclose(eye_g, eye_o, rtol=0, atol=1e-6)
+    e.close()

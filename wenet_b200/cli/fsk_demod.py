@@ -3,13 +3,12 @@
 
 Same argv, input formats, output stream and exit codes as reference src/fsk_demod.c:89-206, demodulating on the
 GPU through libwenet_b200.so.  Differences, all outside the hot path: -l (low-rate mode) and -f (test frames)
-are not implemented and exit 1; the stats JSON (stderr, -t) carries the keys rx/fskstatsudp.py needs
-(EbNodB, ppm, f1_est, f2_est, samp_fft) with EbNodB estimated from the soft decisions and an empty eye diagram;
+are not implemented and exit 1; the stats JSON (stderr, -t) has the reference's keys (secs, EbNodB, ppm, f1_est,
+f2_est[, f3_est, f4_est], eye_diagram, samp_fft -- what rx/fskstatsudp.py parses) but is emitted per block of frames;
 without -s the hard bits are the signs of the soft decisions.  Output is written per block of frames, not per frame.
 """
 import getopt
 import json
-import math
 import signal
 import sys
 import time
@@ -96,7 +95,7 @@ def main(argv=None):
     limits = (o["lo"], o["hi"]) if (o["lo"] > 0 and o["hi"] > o["lo"]) else None
     try:
         eng = E.Engine(1, Fs=o["Fs"], Rs=o["Rs"], M=o["M"], P=o["P"], in_fmt=o["fmt"], framing="none",
-                       chunk_samples=(BLOCK_FRAMES + 2) * 512, est_limits=limits)
+                       chunk_samples=(BLOCK_FRAMES + 2) * 512, est_limits=limits, stats=o["stats"])
     except E.WbError as e:
         sys.stderr.write("Couldn't open files\n%s\n" % e)
         sys.exit(1)
@@ -107,7 +106,6 @@ def main(argv=None):
     dt = E.FMT_DTYPE[o["fmt"]]
     stats_every = int(1 / (o["stats_rate"] * eng.N / o["Fs"])) + 1 if o["stats"] else 0
     frames_since = 0
-    snr_est = 0.0
     while True:
         raw = fin.read(BLOCK_FRAMES * eng.N * bps)
         if not raw:
@@ -127,17 +125,15 @@ def main(argv=None):
             fout.flush()
         if o["stats"] and sd.size:
             frames_since += sd.size // eng.Nbits
-            a = np.abs(sd.astype(np.float64))
-            ebno = -6 + 20 * math.log10((1e-6 + a.mean()) / (1e-6 + a.std()))
-            snr_est = 0.5 * snr_est + 0.5 * ebno
             if frames_since >= stats_every:
                 frames_since = 0
                 st = eng.stats(0)
-                d = {"secs": int(time.time()), "EbNodB": round(snr_est, 1), "ppm": int(st.ppm),
+                d = {"secs": int(time.time()), "EbNodB": round(st.EbNodB, 1), "ppm": int(st.ppm),
                      "f1_est": round(st.f_est[0], 1), "f2_est": round(st.f_est[1], 1)}
                 if o["M"] == 4:
                     d["f3_est"], d["f4_est"] = round(st.f_est[2], 1), round(st.f_est[3], 1)
-                d["eye_diagram"] = []
+                d["eye_diagram"] = [[round(float(st.rx_eye[i][j]), 6) for j in range(st.neyesamp)]
+                                    for i in range(st.neyetr)]
                 d["samp_fft"] = [round(float(v), 6) for v in st.samp_fft[:st.nfft]]
                 sys.stderr.write(json.dumps(d) + "\n")
     fout.flush()

@@ -191,6 +191,7 @@ static int build_fsk_params(const wb_config *cfg, wb_fsk_params *fp)
     fp->f_zero = (int)(((long long)est_space * Ndft) / Fs);
     fp->tc = (float)(0.95 * Ndft / Fs);
     fp->in_fmt = cfg->in_fmt;
+    fp->stats = (cfg->flags & WB_FLAG_STATS) ? 1 : 0;
     switch (cfg->in_fmt) {
     case WB_FMT_CF32: fp->in_bps = 8; break;
     case WB_FMT_CS16: fp->in_bps = 4; break;
@@ -860,14 +861,48 @@ extern "C" int wb_get_stats(wb_engine *e, int stream, wb_stats *out)
     CU(cudaStreamSynchronize(e->stream));
     memset(out, 0, sizeof(*out));
     const float binw = (float)e->fp.Fs / (float)e->fp.Ndft;
+    const int M = e->fp.M, P = e->fp.P;
     out->ppm = st.ppm;
-    for (int m = 0; m < e->fp.M; m++) out->f_est[m] = (float)st.fbin[m] * binw;   /* reference src/fsk.c:671 */
+    for (int m = 0; m < M; m++) out->f_est[m] = (float)st.fbin[m] * binw;   /* reference src/fsk.c:671 */
     out->rx_timing = st.rx_timing;
     out->norm_rx_timing = st.norm_rx_timing;
-    out->foff = 0.0f;
+    {   /* reference src/fsk.c:1026-1029 with f1_tx = 1200, fs_tx = 400 (src/fsk_demod.c:214) */
+        float fc_avg = (out->f_est[0] + out->f_est[1]) / 2;
+        float fc_tx = (float)((1200 + 1200 + 400) / 2);
+        out->foff = fc_tx - fc_avg;
+    }
     out->nin = st.nin;
     out->nfft = e->fp.Ndft / 2;
     memcpy(out->samp_fft, st.fft_est, sizeof(float) * (e->fp.Ndft / 2));
+    if (e->fp.stats && st.eb_count) {
+        /* EbNodB and the snr_est IIR (reference src/fsk.c:1010, :1024), replayed over the last <= 32 frames with the
+           host libm; older frames weigh less than 2^-32 */
+        unsigned n = st.eb_count < 32 ? st.eb_count : 32;
+        float snr = 0.0f;
+        for (unsigned k = 0; k < n; k++) {
+            float a = st.eb_arg[(st.eb_count - n + k) & 31];
+            float ebnodb = -6 + (20 * log10f(a));
+            snr = .5 * snr + .5 * ebnodb;
+        }
+        out->EbNodB = snr;
+        /* eye diagram, reference src/fsk.c:1037-1077.  (The reference indexes f_int with high_sample + 1 + ..., which
+           is negative for rx_timing < -1 and reads outside its array there; those samples are 0 here.) */
+        int dec = (int)ceil(((float)P * 2) / 160);
+        int neyesamp = (P * 2) / dec, traces = 8 / M, off = st.eye_high + 1;
+        out->neyesamp = neyesamp; out->neyetr = M * traces;
+        float emax = 0;
+        for (int i = 0; i < traces; i++)
+            for (int m = 0; m < M; m++)
+                for (int j = 0; j < neyesamp; j++) {
+                    int ind = 2 * P * i + off + j * dec;
+                    float v = 0.0f;
+                    if (ind >= 0 && ind < WB_EYE_KEEP) v = sqrtf(powf(st.eye_fint[m][ind].x, 2.0) + powf(st.eye_fint[m][ind].y, 2.0));
+                    out->rx_eye[i * M + m][j] = v;
+                    if (fabsf(v) > emax) emax = fabsf(v);
+                }
+        for (int i = 0; i < M * traces; i++)
+            for (int j = 0; j < neyesamp; j++) out->rx_eye[i][j] = out->rx_eye[i][j] / emax;
+    }
     out->frames = st.frames;
     out->packets = st.packets;
     out->packet_errors = st.packet_errors;

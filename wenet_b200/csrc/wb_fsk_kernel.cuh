@@ -805,6 +805,52 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 for (int i = lane; i < p.Nbits; i += 32)
                     out[i] = (n_out >= (unsigned)p.Nbits) ? out[i - p.Nbits] : st->sd_last[i];
             }
+            if (p.stats && !(c.flags & 2)) {
+                /* Eb/N0 terms, reference src/fsk.c:985-1010: meanebno / stdebno accumulate over the symbols in order
+                   (every lane repeats the 48-step sum from shuffled-in values), the log10 is left to the host */
+                const int low = c.low, high = c.high;
+                const float fract = c.fract, omf = __fsub_rn(1.0f, fract);
+                float mxv[2] = {0.0f, 0.0f};
+#pragma unroll
+                for (int rr = 0; rr < 2; rr++) {
+                    const int i = lane + 32 * rr;
+                    if (i < p.Nsym) {
+                        const int stt = (i + 1) * p.P;
+                        const int il = wb_phys<SWZ>(stt + low), ih = wb_phys<SWZ>(stt + high);
+                        float mx = 0.0f;
+#pragma unroll
+                        for (int m = 0; m < M; m++) {
+                            const float2 *fi = (m == 0) ? X + xo : Y + (m - 1) * p.ylen;
+                            const float2 lo = fi[il], hi = fi[ih];
+                            const float tr = __fadd_rn(__fmul_rn(omf, lo.x), __fmul_rn(fract, hi.x));
+                            const float ti = __fadd_rn(__fmul_rn(omf, lo.y), __fmul_rn(fract, hi.y));
+                            const float t2 = __fadd_rn(__fmul_rn(tr, tr), __fmul_rn(ti, ti));
+                            mx = (m == 0 || t2 > mx) ? t2 : mx;
+                        }
+                        mxv[rr] = mx;
+                    }
+                }
+                float meane = 0.0f, stde = 0.0f;
+                for (int i = 0; i < p.Nsym; i++) {
+                    const float v = __shfl_sync(0xffffffffu, (i < 32) ? mxv[0] : mxv[1], i & 31);
+                    stde = __fadd_rn(stde, v);
+                    meane = __fadd_rn(meane, __fsqrt_rn(v));
+                }
+                meane = __fdiv_rn(meane, (float)p.Nsym);
+                stde = __fsub_rn(__fdiv_rn(stde, (float)p.Nsym), __fmul_rn(meane, meane));
+                stde = (stde > 0.0f) ? (float)sqrt((double)stde) : 0.0f;
+                if (lane == 0) {
+                    st->eb_arg[st->eb_count & 31] = (float)((1e-6 + (double)meane) / (1e-6 + (double)stde));
+                    st->eb_count = st->eb_count + 1;
+                    st->eye_high = high;
+                }
+                /* eye-diagram tap: the first WB_EYE_KEEP integrator outputs of every tone */
+#pragma unroll
+                for (int m = 0; m < M; m++) {
+                    const float2 *fi = (m == 0) ? X + xo : Y + (m - 1) * p.ylen;
+                    for (int i = lane; i < WB_EYE_KEEP && i < p.nint; i += 32) st->eye_fint[m][i] = fi[wb_phys<SWZ>(i)];
+                }
+            }
             __syncwarp();
             /* old samples for the next frame */
             if (lane < nst) X[lane] = stash;

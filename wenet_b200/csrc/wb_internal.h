@@ -26,6 +26,7 @@
 #define WB_MAX_NIN 512                 /* N + Ts/2 must not exceed this */
 #define WB_MAX_LEVELS 8
 #define WB_MAX_B1W 14
+#define WB_EYE_KEEP 96                 /* integrator outputs kept for the eye diagram: 8/M traces x 2P + offset */
 #define WB_MAX_NINT 496                /* (Nsym + 1) * P <= 49 * 10, rounded */
 #define WB_FRAME_SYMS 48               /* nsyms, reference src/fsk.c:134 */
 #define WB_FSK_THREADS 512             /* 16 stream-warps (2-FSK) / 8 stream-warps x 2 CTAs' worth (4-FSK: 256) */
@@ -49,6 +50,7 @@ struct wb_fsk_params {
     int n_levels;             /* FFT schedule, leaf first */
     int lev_p[WB_MAX_LEVELS], lev_m[WB_MAX_LEVELS], lev_fstride[WB_MAX_LEVELS], lev_sh[WB_MAX_LEVELS];
     int in_fmt, in_bps;       /* bytes per input sample */
+    int stats;                /* WB_FLAG_STATS: per-frame Eb/N0 terms and eye-diagram tap */
     int b1_w;                 /* warps sharing the sequential mixer phase, and their frame segments */
     int b1_seg[WB_MAX_B1W + 1];
     int xlen, ylen, blen, sreg; /* smem geometry per stream: float2 of X, of one other-tone buffer, of all of them
@@ -76,6 +78,13 @@ struct wb_stream_state {
     float  fft_est[WB_MAX_NDFT / 2];
     float2 samp_old[WB_MAX_NSTASH];
     float  sd_last[2 * WB_FRAME_SYMS];   /* last frame's soft decisions: re-emitted when the NaN guard trips, src/fsk.c:878 */
+    /* statistics taps (WB_FLAG_STATS): reference src/fsk.c:995-1080.  eb_arg = (1e-6+mean)/(1e-6+std) of the last 32
+       frames (the host finishes EbNodB = -6 + 20 log10f(.) and the 0.5/0.5 snr_est IIR with its own libm);
+       eye_fint = the first integrator outputs of the last frame, enough for the eye traces */
+    float  eb_arg[32];
+    unsigned int eb_count;
+    int    eye_high;
+    float2 eye_fint[WB_MAXM][WB_EYE_KEEP];
     /* deframer, reference locals of main() src/drs232_ldpc.c:106-118 */
     unsigned long long window;  /* bit_buffer, newest bit = bit 0 */
     int    collecting, ind;
