@@ -19,25 +19,32 @@
  *   CTA = spb streams (runtime; 14 for 2-FSK at Ts = 8 so that two CTAs = 28 streams fit one SM and
  *   4096 streams are all resident on 148 SMs), one "stream warp" per stream, frames in lock step.
  *
- *   A  (stream warps)  bring the frame into shared memory (L2 hits: each frame is prefetched into
- *                      L2 one frame ahead, so HBM latency is off the critical path and no registers
- *                      are tied up), window + 256-point FFT in the reference's butterfly order,
- *                      spectrum IIR (registers), warp-argmax peak picking.
- *   B1 (warp 0, lane = (tone, stream))  ONLY the sequential part of the mixer: oscillator
- *                      recurrence + down-mix product, written in place over the samples.
- *   B2 (stream warps, lanes = integrator outputs)  Ts-tap sums in the reference's ring-buffer slot
- *                      order, in place; |.|^2 summed over tones -> e[i].
- *   B3 (warp 0, lane = (re/im, stream))  the sequential fine-timing accumulation over e[i], then
- *                      atan2 / ppm / nin / resampling offsets on the re-lanes.
+ *   A  (stream warps)  the frame arrives by cp.async (issued at the end of the previous frame; every
+ *                      frame is also prefetched into L2 one frame ahead, so HBM latency is off the
+ *                      critical path and no registers are tied up); window + 256-point FFT in the
+ *                      reference's butterfly order (leaf level fused with the window, top level with
+ *                      |X|^2 and the IIR; bank-conflict-free swizzled work buffer), spectrum IIR in
+ *                      registers, warp-argmax peak picking.
+ *   B1 (warps 0..W-1, lane = (tone, stream))  ONLY the sequential part of the mixer: oscillator
+ *                      recurrence + down-mix product, written in place over the samples.  The
+ *                      recurrence does not depend on the samples, so the W warps all run the same
+ *                      chains and each mixes only its own segment of the frame (see the phase).
+ *   B2 (stream warps, lane = block of Ts integrator outputs)  Ts-tap sums in the reference's
+ *                      ring-buffer slot order, in place; |.|^2 summed over tones; the terms of the
+ *                      fine-timing sum are formed here, in parallel.
+ *   B3 (warp 0, lane = (re/im, stream))  the sequential fine-timing accumulation: only dependent
+ *                      additions are left, in two half-frame passes; then atan2 / ppm / nin /
+ *                      resampling offsets on the re-lanes.
  *   C  (stream warps, lanes = symbols)  linear-interpolated resampling and soft decisions,
- *                      48 (96) floats per frame written coalesced.
+ *                      48 (96) floats per frame written coalesced; next frame's cp.async.
  *
- * The sequential phases cost one warp's issue slots for ALL streams of the CTA (every lane carries
+ * The sequential phases cost a few warps' issue slots for ALL streams of the CTA (every lane carries
  * a different dependent chain); while one CTA of an SM is in B1/B3 the other one runs A/B2/C.
  *
  * Shared memory per stream: X[nst + nmax] float2 (the nst = 2Ts + Ts/2 old samples the mixer can reach
  * back to + the new ones -> tone 0 mixer products -> tone 0 integrator outputs, all in place),
- * Y[(M-1) * ylen] float2 for the other tones (the FFT work buffer in phase A) and E[nint] floats.
+ * Y[(M-1) * ylen] float2 for the other tones (the FFT work buffer in phase A) and E, half a frame of
+ * fine-timing terms (re | im).
  * Stream regions are an odd multiple of 8 bytes mod 128 apart so the lanes of warp 0 (one stream
  * each) hit distinct banks.  For Ts = 8 the mixer products / integrator outputs are stored with
  * their low three index bits XORed with bits 4..6 (wb_phys) so that B2's lanes, which walk blocks
@@ -473,7 +480,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 const float2 dnew = __ldg(&p.dphi[nbn]);
                 const float2 *src = Xs + (nst - nold);
                 float2 *dst = (m == 0) ? Xs + (nst - nold) : Xs + p.xlen + (m - 1) * p.ylen;
-                const int nold_lo = 2 * p.Ts - p.Ts / 2, nold_hi = 2 * p.Ts + p.Ts / 2;
+                const int nold_hi = 2 * p.Ts + p.Ts / 2;          /* >= every possible nold */
                 const int seg0 = p.b1_seg[warp], seg1 = p.b1_seg[warp + 1];
                 /* old -> new samples: comp_normalize + this frame's tone, reference src/fsk.c:787-788 */
 #define WB_B1_SWITCH()                                                                                  \
@@ -551,7 +558,6 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 #undef WB_B1_STEP
 #undef WB_B1_SWITCH
                 if (warp == p.b1_w - 1) c.phi_c[m] = ph;        /* the last segment ends the frame */
-                (void)nold_lo;
             }
         }
         __syncthreads();

@@ -29,7 +29,6 @@
 #define WB_EYE_KEEP 96                 /* integrator outputs kept for the eye diagram: 8/M traces x 2P + offset */
 #define WB_MAX_NINT 496                /* (Nsym + 1) * P <= 49 * 10, rounded */
 #define WB_FRAME_SYMS 48               /* nsyms, reference src/fsk.c:134 */
-#define WB_FSK_THREADS 512             /* 16 stream-warps (2-FSK) / 8 stream-warps x 2 CTAs' worth (4-FSK: 256) */
 
 #define WB_PKT_BODY_BYTES 323          /* 256 payload + 2 crc + 65 parity */
 #define WB_CARRY_CAP 3264              /* >= 3230 symbols of a half-collected v1 packet, 64-float aligned */
