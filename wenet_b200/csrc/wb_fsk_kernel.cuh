@@ -423,11 +423,14 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 #pragma unroll
                 for (int q = 0; q < WB_NEQ; q++)
                     if (lane + 32 * q < nh && v[q] > bv) { bv = v[q]; bi = lane + 32 * q; }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                /* warp argmax, first maximum wins: the values are non-negative floats, which order like their bit
+                   patterns, so two integer warp reductions do it (largest value, then smallest bin holding it) */
+                {
+                    const unsigned vb = __float_as_uint(bv);
+                    const unsigned mx = __reduce_max_sync(0xffffffffu, vb);
+                    const int cand = (vb == mx && mx != 0u) ? bi : 0x7fffffff;
+                    const int bmin = __reduce_min_sync(0xffffffffu, cand);
+                    bi = (mx == 0u) ? 0 : bmin;
                 }
                 const int lo = max(bi - p.f_zero, 0), hi = min(bi + p.f_zero, Ndft);
 #pragma unroll
