@@ -50,13 +50,18 @@ def env_int(name, default):
 
 # ---------------------------------------------------------------- synthetic input
 
-def make_sources(n_src, nsamp, seed_base):
-    """n_src distinct v1 streams (seeded), Eb/N0 cycling through the 4-12 dB sweep."""
+def make_sources(n_src, nsamp, seed_base, mode="v1"):
+    """n_src distinct streams (seeded), Eb/N0 cycling through the 4-12 dB sweep."""
     from wenet_b200 import siggen
     out = []
     for i in range(n_src):
-        raw, _ = siggen.make_stream(seed_base + i, n_samples=nsamp, ebno_db=EBNO_SWEEP[i % len(EBNO_SWEEP)],
-                                    fmt="cf32", clock_ppm=float((i % 7 - 3) * 400))
+        eb = EBNO_SWEEP[i % len(EBNO_SWEEP)]
+        if mode == "fsk4":
+            raw, _ = siggen.make_4fsk_stream(seed_base + i, nsamp // 8 + 16, ebno_db=eb + 3.0)
+            raw = raw[:2 * nsamp]
+        else:
+            raw, _ = siggen.make_stream(seed_base + i, n_samples=nsamp, ebno_db=eb, framing=mode, fmt="cf32",
+                                        clock_ppm=float((i % 7 - 3) * 400))
         out.append(raw)
     return out
 
@@ -223,6 +228,9 @@ def reference_arm(args, rank, world):
 # ---------------------------------------------------------------- this engine
 
 def workload_config(args, world):
+    if args.mode != "v1":
+        return {"workload": "exploration mode %s: %d streams/GPU x %d-sample chunks" % (args.mode, args.streams, args.chunk),
+                "streams_per_gpu": args.streams, "chunk_samples": args.chunk, "in_fmt": "cf32", "mode": args.mode}
     return {"workload": "BASELINE.json configs[3] time-chunked: end-to-end 2-FSK demod + v1 deframe + LDPC(2580,2064) "
                         "max_iter 10 + CRC, %d streams/GPU x %d-sample chunks, Eb/N0 sweep 4-12 dB, Fs 921416 Rs 115177"
                         % (args.streams, args.chunk),
@@ -243,6 +251,9 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=1 << 17, help="samples per stream per e2e step (pinned host)")
     ap.add_argument("--sources", type=int, default=40, help="distinct synthetic streams generated on the host")
     ap.add_argument("--cpu-samples", type=int, default=32 << 20, help="samples per CPU pipe (reference arm)")
+    ap.add_argument("--mode", default="v1", choices=["v1", "v2", "fsk4"],
+                    help="v1 = the headline workload; v2 (960000/96000, wenet_ldpc framing) and fsk4 (4-FSK demod only, "
+                         "BASELINE configs[4]) are exploration modes: no e2e / cpu_baseline, not the graded line")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -286,9 +297,12 @@ def main():
 
     n, chunk = args.streams, args.chunk
     n_src = min(args.sources, n)
-    sources = make_sources(n_src, chunk, seed_base=rank * 1000)
+    sources = make_sources(n_src, chunk, seed_base=rank * 1000, mode=args.mode)
+    if args.mode != "v1":
+        args.no_e2e = args.no_cpu_baseline = True
+    ekw = {"v1": dict(framing="v1"), "v2": dict(Fs=960000, Rs=96000, framing="v2"), "fsk4": dict(M=4, framing="none")}[args.mode]
 
-    eng = E.Engine(n, in_fmt="cf32", framing="v1", chunk_samples=chunk, device=local)
+    eng = E.Engine(n, in_fmt="cf32", chunk_samples=chunk, device=local, **ekw)
     eng.feed(sources + [None] * (n - n_src))
     eng.sync()
     eng.dev_replicate(n_src, chunk, 4096 + 16 * 37)     # stream s = source s % n_src rotated by (s // n_src) * 4688 samples
@@ -338,7 +352,8 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    fsk_gbs = ALG_BYTES_PER_SAMPLE_FSK * samples_step / (kms[0] * 1e-3) / 1e9 if kms[0] > 0 else 0.0
+    alg_bps = 9.0 if args.mode == "fsk4" else ALG_BYTES_PER_SAMPLE_FSK
+    fsk_gbs = alg_bps * samples_step / (kms[0] * 1e-3) / 1e9 if kms[0] > 0 else 0.0
     # DRAM traffic of the dominant kernel per launch: one `ncu --set full` capture of this same workload
     # (profiles/r01_traffic.json says how it was taken); null for any other workload
     traffic = None
@@ -346,7 +361,7 @@ def main():
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
             tj = json.load(fh)
         w = tj["wb_fsk_kernel"]["workload"]
-        if w["streams"] == n and w["chunk_samples"] == chunk and w["in_fmt"] == "cf32":
+        if w["streams"] == n and w["chunk_samples"] == chunk and w["in_fmt"] == "cf32" and args.mode == "v1":
             traffic = tj["wb_fsk_kernel"]["dram_bytes_read"] + tj["wb_fsk_kernel"]["dram_bytes_write"]
     except Exception:
         traffic = None
@@ -355,7 +370,7 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "kernel_ms": {"fsk": round(float(kms[0]), 3), "deframe": round(float(kms[1]), 3),
                               "llr_stats": round(float(kms[2]), 3), "ldpc": round(float(kms[3]), 3)},
-                "alg_bytes_per_launch": ALG_BYTES_PER_SAMPLE_FSK * samples_step}
+                "alg_bytes_per_launch": alg_bps * samples_step}
 
     # ---- e2e through the public API with host buffers ----
     def run_e2e(fmt, ec, n_eng):
