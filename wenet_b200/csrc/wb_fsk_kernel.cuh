@@ -469,10 +469,16 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
            finish together; the redundant recurrences cost issue slots that are idle anyway and cut the
            latency of the phase by about W/2.  (Segments are multiples of 8: the in-place swizzled stores of one
            warp never touch samples another warp still has to read.) */
-        if (warp < p.b1_w && lane < M * spb) {
+        float2 ph_end = make_float2(0.0f, 0.0f);
+        bool ph_store = false;
+        if (warp < p.b1_w) {
             const int m = lane / spb, s = lane - m * spb;
-            wb_fsk_sc &c = sc[s];
-            if (c.flags & 1) {
+            const bool mine = lane < M * spb && (sc[min(s, spb - 1)].flags & 1);
+            /* the tone lanes of one stream read the same samples and tone 0 overwrites them in place: the lanes
+               that take part meet at a __syncwarp between the loads and the stores of every batch */
+            const unsigned bmask = __ballot_sync(0xffffffffu, mine);
+            if (mine) {
+                wb_fsk_sc &c = sc[s];
                 float2 *Xs = reinterpret_cast<float2 *>(regions + (size_t)s * p.sreg);
                 const int fnin = c.nin, nold = p.Nmem - fnin;
                 const int nin_idx = (fnin < p.N) ? 0 : (fnin == p.N ? 1 : 2);
@@ -526,6 +532,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                     float2 xv[8];
 #pragma unroll
                     for (int j = 0; j < 8; j++) xv[j] = src[n0 + j];
+                    __syncwarp(bmask);
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         if (n0 + j == nold) WB_B1_SWITCH();
@@ -541,6 +548,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                     float2 xv[8];
 #pragma unroll
                     for (int j = 0; j < 8; j++) xv[j] = src[n0 + j];
+                    __syncwarp(bmask);
 #pragma unroll
                     for (int j = 0; j < 8; j++) WB_B1_STEP(j);
 #pragma unroll
@@ -553,6 +561,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                     for (int j = 0; n0 + j < seg1; j++) {
                         float2 xv[1];
                         xv[0] = src[n0 + j];
+                        __syncwarp(bmask);
                         if (n0 + j == nold) WB_B1_SWITCH();
                         WB_B1_STEP(0);
                         dst[n0 + (j ^ kb)] = xv[0];
@@ -560,10 +569,13 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 }
 #undef WB_B1_STEP
 #undef WB_B1_SWITCH
-                if (warp == p.b1_w - 1) c.phi_c[m] = ph;        /* the last segment ends the frame */
+                /* the last segment ends the frame; phi_c is stored after the barrier, when every warp has read it */
+                ph_end = ph;
+                ph_store = warp == p.b1_w - 1;
             }
         }
         __syncthreads();
+        if (ph_store) sc[lane % spb].phi_c[lane / spb] = ph_end;
 
         /* ================= B2: stream warps: Ts-tap integrator sums, |.|^2 over tones ================= */
         /* f_int[m][i] = sum of the Ts ring-buffer slots after mixer step i*step + Ts - 1, added in slot order
