@@ -198,14 +198,12 @@ static int build_fsk_params(const wb_config *cfg, wb_fsk_params *fp)
     case WB_FMT_CU8: case WB_FMT_S16: fp->in_bps = 2; break;
     default: return wb_fail(WB_EINVAL, "unknown in_fmt %d", cfg->in_fmt);
     }
-    fp->xlen = (fp->nst + fp->nmax + 1) & ~1;
-    fp->ylen = (fp->nsteps + 1) & ~1;
-    fp->blen = std::max((M - 1) * fp->ylen, Ndft);
-    /* E: nint floats (general P) or two half-frames of re/im terms, (Nsym/2 + 1) blocks of P each */
-    int efl = std::max(fp->nint, 2 * ((fp->Nsym + 2) / 2) * fp->P);
-    int bytes = (fp->xlen + fp->blen) * 8 + ((efl * 4 + 7) & ~7);
-    fp->sreg = (bytes & ~15) + 8;                              /* == 8 (mod 16): lanes of warp 0 hit distinct banks */
-    if (fp->sreg < bytes) fp->sreg += 16;
+    if (Ndft != WB_MAX_NDFT) return wb_fail(WB_EINVAL, "Ndft = %d: the kernels are built for %d", Ndft, WB_MAX_NDFT);
+    /* shared-memory geometry: the formulas the kernel uses (wb_internal.h) */
+    fp->xlen = wb_geom_xlen(Ts);
+    fp->ylen = wb_geom_ylen(Ts, fp->step);
+    fp->blen = wb_geom_blen(M, fp->ylen);
+    fp->sreg = wb_geom_sreg(fp->xlen, fp->blen, wb_geom_efl(P));
     return WB_OK;
 }
 
@@ -359,12 +357,17 @@ static int init_states(wb_engine *e)
     return WB_OK;
 }
 
-template <int M, int TS, bool CF32>
-static cudaError_t fsk_set_attr(size_t smem)
+template <int M, int TS, bool CF32, bool BLK>
+static cudaError_t fsk_set_attr2(size_t smem)
 {
-    cudaError_t ce = cudaFuncSetAttribute(wb_fsk_kernel<M, TS, CF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t ce = cudaFuncSetAttribute(wb_fsk_kernel<M, TS, CF32, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return ce;
-    return cudaFuncSetAttribute(wb_fsk_kernel<M, TS, CF32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    return cudaFuncSetAttribute(wb_fsk_kernel<M, TS, CF32, BLK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+}
+template <int M, int TS, bool CF32>
+static cudaError_t fsk_set_attr(size_t smem, bool blk)
+{
+    return blk ? fsk_set_attr2<M, TS, CF32, true>(smem) : fsk_set_attr2<M, TS, CF32, false>(smem);
 }
 
 extern "C" int wb_create(const wb_config *cfg, wb_engine **out)
@@ -491,12 +494,12 @@ extern "C" int wb_create(const wb_config *cfg, wb_engine **out)
             e->fp.b1_w = W;
         }
         e->fsk_smem = smem_for(spb);
-        const bool cf32 = e->fp.in_fmt == WB_FMT_CF32;
+        const bool cf32 = e->fp.in_fmt == WB_FMT_CF32, blk = e->fp.step == 1;
         cudaError_t ce = cudaErrorInvalidValue;
-        if (e->fp.M == 2 && e->fp.Ts == 8) ce = cf32 ? fsk_set_attr<2, 8, true>(e->fsk_smem) : fsk_set_attr<2, 8, false>(e->fsk_smem);
-        else if (e->fp.M == 2 && e->fp.Ts == 10) ce = cf32 ? fsk_set_attr<2, 10, true>(e->fsk_smem) : fsk_set_attr<2, 10, false>(e->fsk_smem);
-        else if (e->fp.M == 4 && e->fp.Ts == 8) ce = cf32 ? fsk_set_attr<4, 8, true>(e->fsk_smem) : fsk_set_attr<4, 8, false>(e->fsk_smem);
-        else if (e->fp.M == 4 && e->fp.Ts == 10) ce = cf32 ? fsk_set_attr<4, 10, true>(e->fsk_smem) : fsk_set_attr<4, 10, false>(e->fsk_smem);
+        if (e->fp.M == 2 && e->fp.Ts == 8) ce = cf32 ? fsk_set_attr<2, 8, true>(e->fsk_smem, blk) : fsk_set_attr<2, 8, false>(e->fsk_smem, blk);
+        else if (e->fp.M == 2 && e->fp.Ts == 10) ce = cf32 ? fsk_set_attr<2, 10, true>(e->fsk_smem, blk) : fsk_set_attr<2, 10, false>(e->fsk_smem, blk);
+        else if (e->fp.M == 4 && e->fp.Ts == 8) ce = cf32 ? fsk_set_attr<4, 8, true>(e->fsk_smem, blk) : fsk_set_attr<4, 8, false>(e->fsk_smem, blk);
+        else if (e->fp.M == 4 && e->fp.Ts == 10) ce = cf32 ? fsk_set_attr<4, 10, true>(e->fsk_smem, blk) : fsk_set_attr<4, 10, false>(e->fsk_smem, blk);
         else { wb_destroy(e); return wb_fail(WB_EINVAL, "Fs/Rs = %d: only 8 and 10 samples per symbol are built", e->fp.Ts); }
         if (ce != cudaSuccess) { wb_fail(WB_ECUDA, "fsk kernel smem %zu: %s", e->fsk_smem, cudaGetErrorString(ce)); wb_destroy(e); return WB_ECUDA; }
         CRE(cudaFuncSetAttribute(wb_ldpc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(wb_ldpc_smem)));
@@ -608,8 +611,11 @@ template <int M, int TS>
 static void launch_fsk(wb_engine *e, const wb_fsk_args &a)
 {
     const int grid = (e->cfg.n_streams + e->spb - 1) / e->spb;
-    if (e->fp.in_fmt == WB_FMT_CF32) wb_fsk_kernel<M, TS, true><<<grid, e->spb * 32, e->fsk_smem, e->stream>>>(e->fp, a);
-    else wb_fsk_kernel<M, TS, false><<<grid, e->spb * 32, e->fsk_smem, e->stream>>>(e->fp, a);
+    const bool cf32 = e->fp.in_fmt == WB_FMT_CF32, blk = e->fp.step == 1;
+    if (cf32 && blk) wb_fsk_kernel<M, TS, true, true><<<grid, e->spb * 32, e->fsk_smem, e->stream>>>(e->fp, a);
+    else if (cf32) wb_fsk_kernel<M, TS, true, false><<<grid, e->spb * 32, e->fsk_smem, e->stream>>>(e->fp, a);
+    else if (blk) wb_fsk_kernel<M, TS, false, true><<<grid, e->spb * 32, e->fsk_smem, e->stream>>>(e->fp, a);
+    else wb_fsk_kernel<M, TS, false, false><<<grid, e->spb * 32, e->fsk_smem, e->stream>>>(e->fp, a);
 }
 
 /* K2 -> K3 -> K4 -> carry over whatever soft decisions the rows hold (cursor[s].n_sd of them per stream) */
@@ -1204,3 +1210,14 @@ extern "C" int wb_geometry(wb_engine *e, int32_t *out, int n)
     for (int i = 0; i < n && i < 14; i++) out[i] = g[i];
     return WB_OK;
 }
+
+#ifdef WB_PHASE_CLK
+/* debug build only (make dbg -> libwenet_b200_dbg.so): read and clear the per-phase cycle counters of wb_fsk_kernel */
+extern "C" int wb_debug_phase_clk(unsigned long long *out8)
+{
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out8, wb_phase_clk, sizeof(z)) != cudaSuccess) return WB_ECUDA;
+    if (cudaMemcpyToSymbol(wb_phase_clk, z, sizeof(z)) != cudaSuccess) return WB_ECUDA;
+    return WB_OK;
+}
+#endif

@@ -185,10 +185,29 @@ __device__ __forceinline__ int wb_phys(int n)
     return SWZ ? ((n & ~7) | ((n ^ (n >> 4)) & 7)) : n;
 }
 
-template <int M, int TS, bool CF32>
+#ifdef WB_PHASE_CLK
+/* debug build only (make dbg): cycles per phase summed over all CTAs and frames, read with wb_debug_phase_clk */
+__device__ unsigned long long wb_phase_clk[8];
+#define WB_CLK(I) do { if (tid == 0) { const unsigned now_ = (unsigned)clock(); atomicAdd(&wb_phase_clk[I], (unsigned long long)(now_ - clk_prev)); clk_prev = now_; } } while (0)
+#else
+#define WB_CLK(I) do { } while (0)
+#endif
+
+/* BLK: P == Ts (step 1), the configuration every Wenet script uses: the whole frame geometry is a compile-time
+   constant (host and kernel share the wb_blk_* formulas of wb_internal.h).  !BLK: general P, geometry from p. */
+template <int M, int TS, bool CF32, bool BLK>
 __global__ void __launch_bounds__(M == 2 ? 448 : 256, 2)
 wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 {
+    /* frame geometry, reference src/fsk.c:128-259 with nsyms = 48 */
+    constexpr int NSYM = WB_FRAME_SYMS, N_ = TS * NSYM, NMEM = N_ + 2 * TS, NST = 2 * TS + TS / 2, NMAX = N_ + TS / 2;
+    constexpr int NBITS = (M == 2) ? NSYM : 2 * NSYM;
+    constexpr int NDFT = WB_MAX_NDFT, NH = NDFT / 2;
+    static_assert(N_ >= 256 && N_ < 512 && NDFT == 256, "estimator FFT = highest set bit of N = 256 (src/fsk.c:169-173)");
+    constexpr int XLEN = wb_geom_xlen(TS);
+    const int Pc = BLK ? TS : p.P, stepc = BLK ? 1 : p.step, nintc = BLK ? (NSYM + 1) * TS : p.nint;
+    const int ylen = BLK ? wb_blk_ylen(TS) : p.ylen, blen = BLK ? wb_blk_blen(M, TS) : p.blen;
+    const int sreg = BLK ? wb_blk_sreg(M, TS) : p.sreg;
     constexpr int NPRE = (TS * WB_FRAME_SYMS + TS / 2 + 31) / 32;     /* lanes x NPRE >= nmax */
     constexpr bool SWZ = (TS == 8);
     constexpr int NBLK = WB_FRAME_SYMS + 1;                           /* integrator outputs come in 49 blocks of P */
@@ -200,14 +219,15 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     const int spb = a.spb;
     const int sg = blockIdx.x * spb + warp;
     const bool have = sg < a.n_streams;
-    const int Ndft = p.Ndft, nh = Ndft >> 1, nst = p.nst, fmt = p.in_fmt;
+    constexpr int Ndft = NDFT, nh = NH, nst = NST;
+    const int fmt = p.in_fmt;
 
     wb_fsk_sc *sc = reinterpret_cast<wb_fsk_sc *>(wb_fsk_raw);
     float2 *TW = reinterpret_cast<float2 *>(wb_fsk_raw + ((sizeof(wb_fsk_sc) * spb + 127) / 128) * 128);
     unsigned char *regions = reinterpret_cast<unsigned char *>(TW + 3 * (Ndft >> 2));
-    float2 *X = reinterpret_cast<float2 *>(regions + (size_t)warp * p.sreg);
-    float2 *Y = X + p.xlen;
-    float *E = reinterpret_cast<float *>(Y + p.blen);
+    float2 *X = reinterpret_cast<float2 *>(regions + (size_t)warp * sreg);
+    float2 *Y = X + XLEN;
+    float *E = reinterpret_cast<float *>(Y + blen);
 
     /* ---- per-stream state -> registers / shared memory ---- */
     wb_stream_state *st = have ? a.state + sg : nullptr;
@@ -218,7 +238,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     const int sgc = have ? sg : 0;
     unsigned pos = 0, fill = 0, pos0 = 0;
     unsigned frames = 0;
-    int nin = p.N;
+    int nin = N_;
     unsigned n_out = 0;
     float est[WB_NEQ];
     float2 stash = make_float2(0.0f, 0.0f);
@@ -240,7 +260,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     } else if (lane == 0) {
         wb_fsk_sc &c = sc[warp];
         for (int m = 0; m < M; m++) { c.phi_c[m] = make_float2(1.0f, 0.0f); c.pb[m] = 0; c.nb[m] = 0; }
-        c.nin = (short)p.N; c.flags = 0; c.nin_next = (short)p.N; c.norm = 0.0f; c.ppm = 0.0f; c.rx_timing = 0.0f;
+        c.nin = (short)N_; c.flags = 0; c.nin_next = (short)N_; c.norm = 0.0f; c.ppm = 0.0f; c.rx_timing = 0.0f;
         c.low = c.high = 0; c.fract = 0.0f;
     }
     /* cf32: start the copy of the frame at row position POS into X[nst ..] (zeros past the fill mark) */
@@ -249,30 +269,34 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
         int sgv_ = sgc;                                                                                 \
         asm volatile("" : "+r"(sgv_));                                                                  \
         const float2 *row_ = reinterpret_cast<const float2 *>(WB_ROW_IN(sgv_)) + (POS);                 \
-        const int lim_ = (int)min((unsigned)p.nmax, fill > (POS) ? fill - (POS) : 0u);                  \
+        const int lim_ = (int)min((unsigned)NMAX, fill > (POS) ? fill - (POS) : 0u);                  \
         float2 *xd_ = X + nst;                                                                          \
         _Pragma("unroll")                                                                               \
         for (int q_ = 0; q_ < NPRE; q_++) {                                                             \
             const int n_ = lane + 32 * q_;                                                              \
             if (n_ < lim_) wb_cp_async8(xd_ + n_, row_ + n_);                                           \
-            else if (n_ < p.nmax) xd_[n_] = make_float2(0.0f, 0.0f);                                    \
+            else if (n_ < NMAX) xd_[n_] = make_float2(0.0f, 0.0f);                                    \
         }                                                                                               \
     } while (0)
     if (CF32 && have) WB_FETCH_CF32(pos);
 
     const float omt = __fsub_rn(1.0f, p.tc);
-    const bool blocked = (p.step == 1);          /* P == Ts: the configuration every Wenet script uses */
+    constexpr bool blocked = BLK;          /* P == Ts: the configuration every Wenet script uses */
 
+#ifdef WB_PHASE_CLK
+    unsigned clk_prev = (unsigned)clock();
+#endif
     for (;;) {
-        const bool active = have && (pos + (unsigned)nin <= fill) && (n_out + (unsigned)p.Nbits <= a.sd_cap);
+        const bool active = have && (pos + (unsigned)nin <= fill) && (n_out + (unsigned)NBITS <= a.sd_cap);
         if (!__syncthreads_or(active)) break;
+        WB_CLK(6);      /* C + loop barrier */
         const unsigned pos_next = pos + nin;
-        const int xo = nst - (p.Nmem - nin);         /* X index of the first mixer sample */
+        const int xo = nst - (NMEM - nin);         /* X index of the first mixer sample */
 
         /* ================= A: stream warps ================= */
         if (active) {
             /* the leaf butterflies' table entries first: their latency hides behind the landing of the frame */
-            const int pp0 = p.lev_p[0], istr = Ndft / pp0;
+            constexpr int pp0 = 4, istr = Ndft / pp0;            /* 256 = 4 x 4 x 4 x 4, reference src/kiss_fft.c:311-338 */
             const int nwin = min(nin - Ndft, Ndft);
             int lbase[2];
             float lh[2][4];
@@ -303,12 +327,12 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 for (int q = 0; q < NPRE; q++) {
                     const int n = lane + 32 * q;
                     pre_lo[q] = pre_hi[q] = 0u;
-                    if (n < p.nmax && pos + n < fill) wb_load_raw<false>(fmt, in, pos + n, pre_lo[q], pre_hi[q]);
+                    if (n < NMAX && pos + n < fill) wb_load_raw<false>(fmt, in, pos + n, pre_lo[q], pre_hi[q]);
                 }
 #pragma unroll
                 for (int q = 0; q < NPRE; q++) {
                     const int n = lane + 32 * q;
-                    if (n < p.nmax) X[nst + n] = wb_convert<false>(fmt, pre_lo[q], pre_hi[q]);
+                    if (n < NMAX) X[nst + n] = wb_convert<false>(fmt, pre_lo[q], pre_hi[q]);
                 }
             }
             {
@@ -318,7 +342,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 const unsigned char *in = WB_ROW_IN(sgv);
                 const unsigned long long b0 = (unsigned long long)pos_next * p.in_bps;
                 const unsigned long long off = (b0 & ~127ULL) + 128ULL * lane;
-                if (off < b0 + (unsigned long long)p.nmax * p.in_bps && off < (unsigned long long)fill * p.in_bps)
+                if (off < b0 + (unsigned long long)NMAX * p.in_bps && off < (unsigned long long)fill * p.in_bps)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(in + off));
             }
             __syncwarp();
@@ -359,11 +383,13 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 }
             }
             __syncwarp();
-            for (int L = 1; L < p.n_levels - 1; L++) {      /* middle levels: radix 4, twiddles from shared memory */
-                const int sh = p.lev_sh[L], mm = 1 << sh, fs = p.lev_fstride[L];
+#pragma unroll
+            for (int L = 1; L < 3; L++) {                   /* middle levels: radix 4, twiddles from shared memory */
+                const int sh = 2 * L, mm = 1 << sh, fs = Ndft >> (sh + 2);
                 /* m <= 16 < 32: both butterflies of a lane (t = lane, lane + 32) share k and hence the twiddles */
                 const int k = lane & (mm - 1);
                 const float2 w1 = TW[k * fs], w2 = TW[2 * k * fs], w3 = TW[3 * k * fs];
+#pragma unroll
                 for (int t = lane; t < (Ndft >> 2); t += 32) {
                     const int base = ((t >> sh) << (sh + 2)) + k;
                     const int i0 = wb_fidx(base), i1 = wb_fidx(base + mm), i2 = wb_fidx(base + 2 * mm), i3 = wb_fidx(base + 3 * mm);
@@ -460,6 +486,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             sc[warp].flags = 0;
         }
         __syncthreads();
+        WB_CLK(0);
 
         /* ========== B1: warps 0..W-1, lane = (tone, stream): oscillator + down-mix ========== */
         /* The oscillator recurrence is sequential but does not depend on the samples, and a bare recurrence step
@@ -479,17 +506,17 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             const unsigned bmask = __ballot_sync(0xffffffffu, mine);
             if (mine) {
                 wb_fsk_sc &c = sc[s];
-                float2 *Xs = reinterpret_cast<float2 *>(regions + (size_t)s * p.sreg);
-                const int fnin = c.nin, nold = p.Nmem - fnin;
-                const int nin_idx = (fnin < p.N) ? 0 : (fnin == p.N ? 1 : 2);
+                float2 *Xs = reinterpret_cast<float2 *>(regions + (size_t)s * sreg);
+                const int fnin = c.nin, nold = NMEM - fnin;
+                const int nin_idx = (fnin < N_) ? 0 : (fnin == N_ ? 1 : 2);
                 const int pb = c.pb[m], nbn = c.nb[m];
                 float2 ph = c.phi_c[m];
                 ph = wb_cmul2(__ldg(&p.back[nin_idx * nh + pb]), ph);     /* reference src/fsk.c:756-759 */
                 float2 d = __ldg(&p.dphi[pb]);
                 const float2 dnew = __ldg(&p.dphi[nbn]);
                 const float2 *src = Xs + (nst - nold);
-                float2 *dst = (m == 0) ? Xs + (nst - nold) : Xs + p.xlen + (m - 1) * p.ylen;
-                const int nold_hi = 2 * p.Ts + p.Ts / 2;          /* >= every possible nold */
+                float2 *dst = (m == 0) ? Xs + (nst - nold) : Xs + XLEN + (m - 1) * ylen;
+                const int nold_hi = 2 * TS + TS / 2;          /* >= every possible nold */
                 const int seg0 = p.b1_seg[warp], seg1 = p.b1_seg[warp + 1];
                 /* old -> new samples: comp_normalize + this frame's tone, reference src/fsk.c:787-788 */
 #define WB_B1_SWITCH()                                                                                  \
@@ -575,6 +602,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             }
         }
         __syncthreads();
+        WB_CLK(1);
         if (ph_store) sc[lane % spb].phi_c[lane / spb] = ph_end;
 
         /* ================= B2: stream warps: Ts-tap integrator sums, |.|^2 over tones ================= */
@@ -601,7 +629,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 for (int t = 0; t < TS; t++) e[t] = 0.0f;
 #pragma unroll
                 for (int m = 0; m < M; m++) {
-                    float2 *P = (m == 0) ? X + xo : Y + (m - 1) * p.ylen;
+                    float2 *P = (m == 0) ? X + xo : Y + (m - 1) * ylen;
                     float2 vv[2 * TS - 1];
                     if (valid) {
                         const int k0 = SWZ ? ((u >> 1) & 7) : 0, k1 = SWZ ? (((u + 1) >> 1) & 7) : 0;
@@ -666,17 +694,17 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             }
         } else if (active) {
             /* general P: lanes = outputs, ring slots by modular arithmetic, E linear */
-            const int step = p.step;
-            for (int i0 = 0; i0 < p.nint; i0 += 32) {
+            const int step = stepc;
+            for (int i0 = 0; i0 < nintc; i0 += 32) {
                 const int i = i0 + lane;
-                const bool valid = i < p.nint;
+                const bool valid = i < nintc;
                 float2 f[M];
                 float e = 0.0f;
                 if (valid) {
                     const int n0 = i * step, r = n0 % TS;
 #pragma unroll
                     for (int m = 0; m < M; m++) {
-                        const float2 *P = (m == 0) ? X + xo : Y + (m - 1) * p.ylen;
+                        const float2 *P = (m == 0) ? X + xo : Y + (m - 1) * ylen;
                         float sr = 0.0f, si = 0.0f;
 #pragma unroll
                         for (int j = 0; j < TS; j++) {
@@ -695,7 +723,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 if (valid) {
 #pragma unroll
                     for (int m = 0; m < M; m++) {
-                        float2 *P = (m == 0) ? X + xo : Y + (m - 1) * p.ylen;
+                        float2 *P = (m == 0) ? X + xo : Y + (m - 1) * ylen;
                         P[wb_phys<SWZ>(i)] = f[m];
                     }
                     E[i] = e;
@@ -704,6 +732,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             }
         }
         __syncthreads();
+        WB_CLK(2);
 
         /* ============ B3: warp 0, lane = (re/im, stream): fine-timing accumulation ============ */
         /* t_c = sum_i e_i * phi_ft[i] is strictly sequential (reference src/fsk.c:858-873).  With the terms already
@@ -714,7 +743,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
         const int b3c = (lane < spb) ? 0 : 1, b3s = min(lane - b3c * spb, spb - 1);
         const bool b3_lane = (warp == 0) && (lane < 2 * spb) && (sc[b3s].flags & 1);
         const float *Es = reinterpret_cast<const float *>(
-            reinterpret_cast<const float2 *>(regions + (size_t)b3s * p.sreg) + p.xlen + p.blen);
+            reinterpret_cast<const float2 *>(regions + (size_t)b3s * sreg) + XLEN + blen);
         if (blocked) {
 #define WB_B3_PASS(NB)                                                                                  \
             do {                                                                                        \
@@ -739,6 +768,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             } while (0)
             WB_B3_PASS(B3H);
             __syncthreads();
+            WB_CLK(3);
             if (active && dblk >= 0) {
                 float2 *er = reinterpret_cast<float2 *>(E) + dblk * (TS / 2);
                 float2 *ei = reinterpret_cast<float2 *>(E + B3E) + dblk * (TS / 2);
@@ -750,10 +780,11 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 }
             }
             __syncthreads();
+            WB_CLK(4);
             WB_B3_PASS(NBLK - B3H);
 #undef WB_B3_PASS
         } else if (b3_lane) {
-            for (int i = 0; i < p.nint; i++) {
+            for (int i = 0; i < nintc; i++) {
                 const float2 t2 = p.pftc[i];
                 tacc = __fadd_rn(tacc, __fmul_rn(Es[i], b3c ? t2.y : t2.x));          /* reference src/fsk.c:870 */
             }
@@ -766,16 +797,16 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 const bool nan = isnan(tcr) || isnan(tci);     /* reference src/fsk.c:878-880 */
                 if (!nan) {
                     const float norm = (float)((double)wb_atan2f(tci, tcr) / 6.283185307179586);
-                    const float rx_timing = __fmul_rn(norm, (float)p.P);
+                    const float rx_timing = __fmul_rn(norm, (float)Pc);
                     const float dn = __fsub_rn(norm, c.norm);
                     c.norm = norm;
                     if ((double)fabsf(dn) < .2) {
-                        const float appm = (float)(1e6 * (double)dn / (double)(float)p.Nsym);
+                        const float appm = (float)(1e6 * (double)dn / (double)(float)NSYM);
                         c.ppm = (float)(.9 * (double)c.ppm + .1 * (double)appm);
                     }
-                    if ((double)norm > 0.25) c.nin_next = (short)(p.N + p.Ts / 2);
-                    else if ((double)norm < -0.25) c.nin_next = (short)(p.N - p.Ts / 2);
-                    else c.nin_next = (short)p.N;
+                    if ((double)norm > 0.25) c.nin_next = (short)(N_ + TS / 2);
+                    else if ((double)norm < -0.25) c.nin_next = (short)(N_ - TS / 2);
+                    else c.nin_next = (short)N_;
                     const int low = (int)floorf(rx_timing);
                     c.low = (short)low;
                     c.fract = __fsub_rn(rx_timing, (float)low);
@@ -788,6 +819,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             }
         }
         __syncthreads();
+        WB_CLK(5);
 
         /* ================= C: stream warps, lanes = symbols ================= */
         if (active) {
@@ -798,13 +830,13 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             if (!(c.flags & 2)) {
                 const int low = c.low, high = c.high;
                 const float fract = c.fract, omf = __fsub_rn(1.0f, fract);
-                for (int i = lane; i < p.Nsym; i += 32) {
-                    const int stt = (i + 1) * p.P;
+                for (int i = lane; i < NSYM; i += 32) {
+                    const int stt = (i + 1) * Pc;
                     const int il = wb_phys<SWZ>(stt + low), ih = wb_phys<SWZ>(stt + high);
                     float tm[M];
 #pragma unroll
                     for (int m = 0; m < M; m++) {
-                        const float2 *fi = (m == 0) ? X + xo : Y + (m - 1) * p.ylen;
+                        const float2 *fi = (m == 0) ? X + xo : Y + (m - 1) * ylen;
                         const float2 lo = fi[il], hi = fi[ih];
                         const float tr = __fadd_rn(__fmul_rn(omf, lo.x), __fmul_rn(fract, hi.x));
                         const float ti = __fadd_rn(__fmul_rn(omf, lo.y), __fmul_rn(fract, hi.y));
@@ -823,8 +855,8 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             } else {
                 /* NaN guard: the reference returns before writing, so the caller's buffer still holds
                    the previous frame's values (zeros before the first frame) */
-                for (int i = lane; i < p.Nbits; i += 32)
-                    out[i] = (n_out >= (unsigned)p.Nbits) ? out[i - p.Nbits] : st->sd_last[i];
+                for (int i = lane; i < NBITS; i += 32)
+                    out[i] = (n_out >= (unsigned)NBITS) ? out[i - NBITS] : st->sd_last[i];
             }
             if (p.stats && !(c.flags & 2)) {
                 /* Eb/N0 terms, reference src/fsk.c:985-1010: meanebno / stdebno accumulate over the symbols in order
@@ -835,13 +867,13 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 #pragma unroll
                 for (int rr = 0; rr < 2; rr++) {
                     const int i = lane + 32 * rr;
-                    if (i < p.Nsym) {
-                        const int stt = (i + 1) * p.P;
+                    if (i < NSYM) {
+                        const int stt = (i + 1) * Pc;
                         const int il = wb_phys<SWZ>(stt + low), ih = wb_phys<SWZ>(stt + high);
                         float mx = 0.0f;
 #pragma unroll
                         for (int m = 0; m < M; m++) {
-                            const float2 *fi = (m == 0) ? X + xo : Y + (m - 1) * p.ylen;
+                            const float2 *fi = (m == 0) ? X + xo : Y + (m - 1) * ylen;
                             const float2 lo = fi[il], hi = fi[ih];
                             const float tr = __fadd_rn(__fmul_rn(omf, lo.x), __fmul_rn(fract, hi.x));
                             const float ti = __fadd_rn(__fmul_rn(omf, lo.y), __fmul_rn(fract, hi.y));
@@ -852,13 +884,13 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                     }
                 }
                 float meane = 0.0f, stde = 0.0f;
-                for (int i = 0; i < p.Nsym; i++) {
+                for (int i = 0; i < NSYM; i++) {
                     const float v = __shfl_sync(0xffffffffu, (i < 32) ? mxv[0] : mxv[1], i & 31);
                     stde = __fadd_rn(stde, v);
                     meane = __fadd_rn(meane, __fsqrt_rn(v));
                 }
-                meane = __fdiv_rn(meane, (float)p.Nsym);
-                stde = __fsub_rn(__fdiv_rn(stde, (float)p.Nsym), __fmul_rn(meane, meane));
+                meane = __fdiv_rn(meane, (float)NSYM);
+                stde = __fsub_rn(__fdiv_rn(stde, (float)NSYM), __fmul_rn(meane, meane));
                 stde = (stde > 0.0f) ? (float)sqrt((double)stde) : 0.0f;
                 if (lane == 0) {
                     st->eb_arg[st->eb_count & 31] = (float)((1e-6 + (double)meane) / (1e-6 + (double)stde));
@@ -868,8 +900,8 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 /* eye-diagram tap: the first WB_EYE_KEEP integrator outputs of every tone */
 #pragma unroll
                 for (int m = 0; m < M; m++) {
-                    const float2 *fi = (m == 0) ? X + xo : Y + (m - 1) * p.ylen;
-                    for (int i = lane; i < WB_EYE_KEEP && i < p.nint; i += 32) st->eye_fint[m][i] = fi[wb_phys<SWZ>(i)];
+                    const float2 *fi = (m == 0) ? X + xo : Y + (m - 1) * ylen;
+                    for (int i = lane; i < WB_EYE_KEEP && i < nintc; i += 32) st->eye_fint[m][i] = fi[wb_phys<SWZ>(i)];
                 }
             }
             __syncwarp();
@@ -890,7 +922,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                     l[5] = c.norm; l[6] = c.ppm; l[7] = c.rx_timing;
                 }
             }
-            n_out += p.Nbits;
+            n_out += NBITS;
             pos = pos_next;
             nin = c.nin_next;
             frames++;
@@ -905,9 +937,9 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
         for (int q = 0; q < WB_NEQ; q++)
             if (lane + 32 * q < nh) st->fft_est[lane + 32 * q] = est[q];
         if (lane < nst) st->samp_old[lane] = X[lane];
-        if (n_out >= (unsigned)p.Nbits) {
-            const float *lastf = WB_ROW_SD(sg) + n_out - p.Nbits;
-            for (int i = lane; i < p.Nbits; i += 32) st->sd_last[i] = lastf[i];
+        if (n_out >= (unsigned)NBITS) {
+            const float *lastf = WB_ROW_SD(sg) + n_out - NBITS;
+            for (int i = lane; i < NBITS; i += 32) st->sd_last[i] = lastf[i];
         }
         const unsigned char *in = WB_ROW_IN(sg);
         const unsigned long long rem = fill - pos;

@@ -37,6 +37,29 @@
 #define WB_LDPC_SLOTS 14               /* edge slots per check: 12 H1 + parity j-1 + parity j */
 #define WB_LDPC_NMSG (WB_LDPC_SLOTS * WB_NPAR)   /* 7224 message words (slot 12 of check 0 is unused) */
 
+/* shared-memory geometry of wb_fsk_kernel per stream, one formula for host (build_fsk_params) and kernel:
+   xlen = float2 of X (old + new samples), ylen = float2 of one other-tone buffer, blen = float2 of all of them
+   (>= Ndft: the FFT work buffer), efl = floats of E, sreg = bytes per stream region (== 8 mod 16, so the
+   lanes of a sequential-phase warp, one stream each, hit distinct banks).  wb_blk_* : P == Ts. */
+#ifdef __CUDACC__
+#define WB_HD __host__ __device__
+#else
+#define WB_HD
+#endif
+WB_HD constexpr int wb_geom_xlen(int Ts) { return ((2 * Ts + Ts / 2) + (Ts * WB_FRAME_SYMS + Ts / 2) + 1) & ~1; }
+WB_HD constexpr int wb_geom_ylen(int Ts, int step) { return ((Ts * WB_FRAME_SYMS + 2 * Ts - step) + 1) & ~1; }
+WB_HD constexpr int wb_geom_blen(int M, int ylen) { return (M - 1) * ylen > WB_MAX_NDFT ? (M - 1) * ylen : WB_MAX_NDFT; }
+WB_HD constexpr int wb_geom_efl(int P) { return (WB_FRAME_SYMS + 1) * P > 2 * ((WB_FRAME_SYMS + 2) / 2) * P ? (WB_FRAME_SYMS + 1) * P : 2 * ((WB_FRAME_SYMS + 2) / 2) * P; }
+WB_HD constexpr int wb_geom_sreg(int xlen, int blen, int efl)
+{
+    const int bytes = (xlen + blen) * 8 + ((efl * 4 + 7) & ~7);
+    const int sreg = (bytes & ~15) + 8;
+    return sreg < bytes ? sreg + 16 : sreg;
+}
+WB_HD constexpr int wb_blk_ylen(int Ts) { return wb_geom_ylen(Ts, 1); }
+WB_HD constexpr int wb_blk_blen(int M, int Ts) { return wb_geom_blen(M, wb_blk_ylen(Ts)); }
+WB_HD constexpr int wb_blk_sreg(int M, int Ts) { return wb_geom_sreg(wb_geom_xlen(Ts), wb_blk_blen(M, Ts), wb_geom_efl(Ts)); }
+
 struct wb_fsk_params {
     int Fs, Rs, Ts, P, M, N, Nsym, Nmem, Nbits, Ndft, nstash;
     int nst;                  /* 2*Ts + Ts/2: old samples the mixer can reach back to (<= nstash = 4*Ts) */
