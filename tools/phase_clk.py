@@ -29,7 +29,7 @@ for it in range(3):
     ms = eng.last_kernel_ms()
     frames = chunk / 384.0
     ctas = (n + 13) // 14
-    names = ["A", "B1", "B2", "B3a", "swap", "B3b+atan", "C+loop"]
+    names = ["A", "B1", "B2", "B3", "-", "-", "C+loop"]
     print("fsk %.2f ms; cycles per CTA-frame: " % ms[0] +
           ", ".join("%s %.0f" % (nm, x / ctas / frames) for nm, x in zip(names, v)) +
           "; total %.0f" % (v.sum() / ctas / frames))

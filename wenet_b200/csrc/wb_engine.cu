@@ -255,7 +255,7 @@ static int upload_tables(wb_engine *e)
     {
         hcpx d = hcexpj((float)(2 * M_PI * ((float)fp.Rs / (float)(fp.P * fp.Rs))));
         hcpx ph; ph.r = 1; ph.i = 0;
-        for (int i = 0; i < fp.nint; i++) { pft[i] = ph; fp.pftc[i] = make_float2(ph.r, ph.i); ph = hcmul(ph, d); }
+        for (int i = 0; i < fp.nint; i++) { pft[i] = ph; ((float *)fp.pftc4[0])[i] = ph.r; ((float *)fp.pftc4[1])[i] = ph.i; ph = hcmul(ph, d); }
     }
     /* per-bin tone oscillators, reference src/fsk.c:756-764, :671 */
     for (int b = 0; b < nh; b++) {
@@ -467,10 +467,10 @@ extern "C" int wb_create(const wb_config *cfg, wb_engine **out)
                                               (size_t)spb * e->fp.sreg; };
         int spb = 0;
         for (int ctas = 2; ctas >= 1 && spb == 0; ctas--)
-            for (int t = max_spb; t >= (ctas == 2 ? 4 : 1); t--)
+            for (int t = max_spb; t >= (ctas == 2 ? 4 : 2); t--)      /* >= 2: the re and im fine-timing chains run in warps 0 and 1 */
                 if (smem_for(t) <= (size_t)dev_smem_blk && ctas * (smem_for(t) + 1024) <= (size_t)dev_smem_sm) { spb = t; break; }
         if (spb == 0) { wb_destroy(e); return wb_fail(WB_EINVAL, "FSK kernel does not fit shared memory"); }
-        if (getenv("WB_FSK_SPB")) spb = std::max(1, std::min(max_spb, atoi(getenv("WB_FSK_SPB"))));
+        if (getenv("WB_FSK_SPB")) spb = std::max(2, std::min(max_spb, atoi(getenv("WB_FSK_SPB"))));
         e->spb = spb;
         /* segments of the sequential mixer phase (see wb_fsk_kernel.cuh, B1): multiples of 8 steps, shrinking
            geometrically by the cost ratio (bare recurrence step) / (recurrence + mix step) */

@@ -64,11 +64,11 @@ struct wb_fsk_sc {                 /* per-stream frame scalars in shared memory 
     float2 phi_c[WB_MAXM];
     short pb[WB_MAXM];             /* estimator bins in force before this frame (fsk->f_est) */
     short nb[WB_MAXM];             /* bins estimated from this frame */
-    short nin, nin_next;
-    short low, high;
-    int flags;                     /* bit 0 = active this frame, bit 1 = NaN guard tripped */
-    float fract, norm, ppm, rx_timing;
-    int pad;
+    short nin, pad0;
+    int flags;                     /* bit 0 = active this frame */
+    float tcr, tci;                /* fine-timing sum t_c of this frame (B3 -> C) */
+    float norm, ppm, rx_timing;
+    int pad1;
 };
 static_assert(sizeof(wb_fsk_sc) == 80, "shared-memory budget of wb_fsk_kernel");
 
@@ -185,6 +185,28 @@ __device__ __forceinline__ int wb_phys(int n)
     return SWZ ? ((n & ~7) | ((n ^ (n >> 4)) & 7)) : n;
 }
 
+/* NB blocks of the fine-timing sum t_c += e_i * phi_ft[i] (reference src/fsk.c:870-873) for one component:
+   q_ = the blocks' e pairs (pair q of block b at b*TS/2 + (q ^ key(b))), c4 = that component of phi_ft.  The
+   multiplies are off the dependent chain of additions. */
+__device__ __forceinline__ float wb_f4c(const float4 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+template <int TS, int NB, bool SWZ8>
+__device__ __forceinline__ float wb_b3_group(const float2 *q_, const float4 *c4, float tacc)
+{
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const int key = SWZ8 ? ((b >> 2) & 3) : 0;
+#pragma unroll
+        for (int q = 0; q < TS / 2; q++) {
+            const float2 ev = q_[b * (TS / 2) + (q ^ key)];
+            const int i = b * TS + 2 * q;
+            const float4 ca = c4[i >> 2], cb = c4[(i + 1) >> 2];
+            tacc = __fadd_rn(tacc, __fmul_rn(ev.x, wb_f4c(ca, i & 3)));
+            tacc = __fadd_rn(tacc, __fmul_rn(ev.y, wb_f4c(cb, (i + 1) & 3)));
+        }
+    }
+    return tacc;
+}
+
 #ifdef WB_PHASE_CLK
 /* debug build only (make dbg): cycles per phase summed over all CTAs and frames, read with wb_debug_phase_clk */
 __device__ unsigned long long wb_phase_clk[8];
@@ -211,8 +233,6 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     constexpr int NPRE = (TS * WB_FRAME_SYMS + TS / 2 + 31) / 32;     /* lanes x NPRE >= nmax */
     constexpr bool SWZ = (TS == 8);
     constexpr int NBLK = WB_FRAME_SYMS + 1;                           /* integrator outputs come in 49 blocks of P */
-    constexpr int B3H = NBLK / 2;                                     /* blocks in the first pass of B3 (24) */
-    constexpr int B3E = (NBLK - B3H) * TS;                            /* floats per component half in E (200) */
     constexpr bool B3SWZ = (TS == 8);                                 /* 4 pairs per block: XOR-swizzle the pair index */
     extern __shared__ __align__(16) unsigned char wb_fsk_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -255,13 +275,12 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             wb_fsk_sc &c = sc[warp];
             for (int m = 0; m < M; m++) { c.phi_c[m] = st->phi_c[m]; c.pb[m] = (short)st->fbin[m]; c.nb[m] = 0; }
             c.norm = st->norm_rx_timing; c.ppm = st->ppm; c.rx_timing = st->rx_timing;
-            c.nin = (short)nin; c.nin_next = (short)nin; c.flags = 0; c.low = c.high = 0; c.fract = 0.0f;
+            c.nin = (short)nin; c.flags = 0; c.tcr = c.tci = 0.0f;
         }
     } else if (lane == 0) {
         wb_fsk_sc &c = sc[warp];
         for (int m = 0; m < M; m++) { c.phi_c[m] = make_float2(1.0f, 0.0f); c.pb[m] = 0; c.nb[m] = 0; }
-        c.nin = (short)N_; c.flags = 0; c.nin_next = (short)N_; c.norm = 0.0f; c.ppm = 0.0f; c.rx_timing = 0.0f;
-        c.low = c.high = 0; c.fract = 0.0f;
+        c.nin = (short)N_; c.flags = 0; c.norm = 0.0f; c.ppm = 0.0f; c.rx_timing = 0.0f; c.tcr = c.tci = 0.0f;
     }
     /* cf32: start the copy of the frame at row position POS into X[nst ..] (zeros past the fill mark) */
 #define WB_FETCH_CF32(POS)                                                                              \
@@ -609,16 +628,11 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
         /* f_int[m][i] = sum of the Ts ring-buffer slots after mixer step i*step + Ts - 1, added in slot order
            (reference src/fsk.c:835-838): slot j holds the product of the step n in [i*step, i*step + Ts) with
            n mod Ts == j.  In place: output i overwrites product i. */
-        /* terms of the fine-timing sum of the one block per lane that belongs to the second pass of B3 */
-        float dre[TS], dim[TS];
-        int dblk = -1;
-#pragma unroll
-        for (int t = 0; t < TS; t++) { dre[t] = 0.0f; dim[t] = 0.0f; }
         if (active && blocked) {
             /* step = 1: lane u owns outputs Ts*u .. Ts*u + Ts - 1.  It needs products Ts*u .. Ts*u + 2Ts - 2; output
                Ts*u + t adds, in slot order, the first t products of block u+1 (a running prefix shared by all t)
-               and then products t .. Ts-1 of block u.  The terms of the fine-timing sum, e * phi_ft (reference
-               src/fsk.c:870), are formed here in parallel and handed to B3 through E in two halves. */
+               and then products t .. Ts-1 of block u.  e_i = sum over tones of |f_int|^2 (reference src/fsk.c:864-867)
+               goes to B3 through E. */
             static_assert(NBLK <= 64, "two rounds of 32 lanes cover the blocks");
 #pragma unroll
             for (int rr = 0; rr < 2; rr++) {
@@ -663,33 +677,12 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                     __syncwarp();
                 }
                 if (valid) {
-                    /* blocks 0..B3H-1 feed the first pass of B3 (E = [re terms | im terms], in output order);
-                       a lane owns at most one later block (lanes 24..31 in round 0, lanes 0..16 in round 1):
-                       its terms wait in registers */
-                    /* E = [re terms | im terms], B3E floats each, a block's TS terms stored as float2 pairs at pair
-                       index (p ^ key), key = (block >> 2) & 3: conflict-free stores here, aligned 8-byte loads in B3 */
-                    const float2 *pf = p.pft + u * TS;
-                    float tr[TS], ti[TS];
+                    /* E: block u = TS/2 float2 pairs at pair index (q ^ key), key = (u >> 2) & 3 for Ts = 8:
+                       conflict-free 8-byte stores here, aligned 8-byte loads in B3 */
+                    float2 *eo = reinterpret_cast<float2 *>(E) + u * (TS / 2);
+                    const int key = B3SWZ ? ((u >> 2) & 3) : 0;
 #pragma unroll
-                    for (int t = 0; t < TS; t++) {
-                        const float2 w = wb_ldg_keep2(pf + t);
-                        tr[t] = __fmul_rn(e[t], w.x);                              /* reference src/fsk.c:870 */
-                        ti[t] = __fmul_rn(e[t], w.y);
-                    }
-                    if (u < B3H) {
-                        float2 *er = reinterpret_cast<float2 *>(E) + u * (TS / 2);
-                        float2 *ei = reinterpret_cast<float2 *>(E + B3E) + u * (TS / 2);
-                        const int key = B3SWZ ? ((u >> 2) & 3) : 0;
-#pragma unroll
-                        for (int q = 0; q < TS / 2; q++) {
-                            er[q ^ key] = make_float2(tr[2 * q], tr[2 * q + 1]);
-                            ei[q ^ key] = make_float2(ti[2 * q], ti[2 * q + 1]);
-                        }
-                    } else {
-                        dblk = u - B3H;
-#pragma unroll
-                        for (int t = 0; t < TS; t++) { dre[t] = tr[t]; dim[t] = ti[t]; }
-                    }
+                    for (int q = 0; q < TS / 2; q++) eo[q ^ key] = make_float2(e[2 * q], e[2 * q + 1]);
                 }
             }
         } else if (active) {
@@ -734,102 +727,76 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
         __syncthreads();
         WB_CLK(2);
 
-        /* ============ B3: warp 0, lane = (re/im, stream): fine-timing accumulation ============ */
-        /* t_c = sum_i e_i * phi_ft[i] is strictly sequential (reference src/fsk.c:858-873).  With the terms already
-           formed by B2, what is left per output is one load and one dependent addition per component, and the two
-           components run in different lanes.  E holds half a frame of terms at a time ([re | im], output order):
-           pass 1 = blocks 0..23, then the stream warps drop in blocks 24..48, pass 2. */
-        float tacc = 0.0f;
-        const int b3c = (lane < spb) ? 0 : 1, b3s = min(lane - b3c * spb, spb - 1);
-        const bool b3_lane = (warp == 0) && (lane < 2 * spb) && (sc[b3s].flags & 1);
-        const float *Es = reinterpret_cast<const float *>(
-            reinterpret_cast<const float2 *>(regions + (size_t)b3s * sreg) + XLEN + blen);
+        /* ============ B3: warp 0 = re, warp 1 = im, lane = stream: fine-timing accumulation ============ */
+        /* t_c = sum_i e_i * phi_ft[i] is strictly sequential (reference src/fsk.c:858-873): one dependent addition
+           per output and component.  The two components run in two warps; phi_ft is a compile-time index into the
+           kernel-parameter constant bank, so a step is one multiply (off the chain) and one add (on it), and the
+           e_i arrive by 8-byte loads the compiler hoists ahead of the chain. */
         if (blocked) {
-#define WB_B3_PASS(NB)                                                                                  \
-            do {                                                                                        \
-                if (b3_lane) {                                                                          \
-                    const float2 *q_ = reinterpret_cast<const float2 *>(Es + b3c * B3E);                \
-                    float2 ev[TS / 2], en[TS / 2];                                                      \
-                    _Pragma("unroll")                                                                   \
-                    for (int t = 0; t < TS / 2; t++) ev[t] = q_[t];            /* block 0: key 0 */     \
-                    _Pragma("unroll 1")                                                                 \
-                    for (int u = 0; u < (NB); u++) {                                                    \
-                        /* the next block's terms are on their way while this block's additions run */ \
-                        const int un_ = (u + 1 < (NB)) ? u + 1 : u;                                     \
-                        const int key_ = B3SWZ ? ((un_ >> 2) & 3) : 0;                                  \
-                        _Pragma("unroll")                                                               \
-                        for (int t = 0; t < TS / 2; t++) en[t] = q_[un_ * (TS / 2) + (t ^ key_)];       \
-                        _Pragma("unroll")                                                               \
-                        for (int t = 0; t < TS / 2; t++) { tacc = __fadd_rn(tacc, ev[t].x); tacc = __fadd_rn(tacc, ev[t].y); } \
-                        _Pragma("unroll")                                                               \
-                        for (int t = 0; t < TS / 2; t++) ev[t] = en[t];                                 \
-                    }                                                                                   \
-                }                                                                                       \
-            } while (0)
-            WB_B3_PASS(B3H);
-            __syncthreads();
-            WB_CLK(3);
-            if (active && dblk >= 0) {
-                float2 *er = reinterpret_cast<float2 *>(E) + dblk * (TS / 2);
-                float2 *ei = reinterpret_cast<float2 *>(E + B3E) + dblk * (TS / 2);
-                const int key = B3SWZ ? ((dblk >> 2) & 3) : 0;
-#pragma unroll
-                for (int q = 0; q < TS / 2; q++) {
-                    er[q ^ key] = make_float2(dre[2 * q], dre[2 * q + 1]);
-                    ei[q ^ key] = make_float2(dim[2 * q], dim[2 * q + 1]);
+            if (warp < 2) {
+                const int s = min(lane, spb - 1);
+                if (lane < spb && (sc[s].flags & 1)) {
+                    const float2 *q_ = reinterpret_cast<const float2 *>(
+                        reinterpret_cast<const float2 *>(regions + (size_t)s * sreg) + XLEN + blen);
+                    const float4 *c4 = p.pftc4[warp];              /* warp 0: real parts, warp 1: imaginary parts */
+                    float tacc = 0.0f;
+                    /* groups of 16 blocks (the period of the swizzle key): a loop body small enough to stay in the
+                       instruction cache -- one warp running straight-line code has nobody to hide its fetches */
+#pragma unroll 1
+                    for (int g = 0; g < NBLK / 16; g++)
+                        tacc = wb_b3_group<TS, 16, B3SWZ>(q_ + g * 16 * (TS / 2), c4 + g * 16 * TS / 4, tacc);
+                    tacc = wb_b3_group<TS, NBLK % 16, B3SWZ>(q_ + (NBLK / 16) * 16 * (TS / 2), c4 + (NBLK / 16) * 16 * TS / 4, tacc);
+                    if (warp == 0) sc[s].tcr = tacc; else sc[s].tci = tacc;
                 }
             }
-            __syncthreads();
-            WB_CLK(4);
-            WB_B3_PASS(NBLK - B3H);
-#undef WB_B3_PASS
-        } else if (b3_lane) {
-            for (int i = 0; i < nintc; i++) {
-                const float2 t2 = p.pftc[i];
-                tacc = __fadd_rn(tacc, __fmul_rn(Es[i], b3c ? t2.y : t2.x));          /* reference src/fsk.c:870 */
-            }
-        }
-        if (warp == 0) {
-            const float tcr = __shfl_sync(0xffffffffu, tacc, b3s);
-            const float tci = __shfl_sync(0xffffffffu, tacc, min(spb + b3s, 31));
-            if (b3_lane && b3c == 0) {
-                wb_fsk_sc &c = sc[b3s];
-                const bool nan = isnan(tcr) || isnan(tci);     /* reference src/fsk.c:878-880 */
-                if (!nan) {
-                    const float norm = (float)((double)wb_atan2f(tci, tcr) / 6.283185307179586);
-                    const float rx_timing = __fmul_rn(norm, (float)Pc);
-                    const float dn = __fsub_rn(norm, c.norm);
-                    c.norm = norm;
-                    if ((double)fabsf(dn) < .2) {
-                        const float appm = (float)(1e6 * (double)dn / (double)(float)NSYM);
-                        c.ppm = (float)(.9 * (double)c.ppm + .1 * (double)appm);
-                    }
-                    if ((double)norm > 0.25) c.nin_next = (short)(N_ + TS / 2);
-                    else if ((double)norm < -0.25) c.nin_next = (short)(N_ - TS / 2);
-                    else c.nin_next = (short)N_;
-                    const int low = (int)floorf(rx_timing);
-                    c.low = (short)low;
-                    c.fract = __fsub_rn(rx_timing, (float)low);
-                    c.high = (short)(int)ceilf(rx_timing);
-                    c.rx_timing = rx_timing;
-                } else {
-                    c.flags = 3;
-                    c.nin_next = c.nin;
+        } else if (warp == 0) {
+            /* general P: lane = (re/im, stream) */
+            const int b3c = (lane < spb) ? 0 : 1, b3s = min(lane - b3c * spb, spb - 1);
+            if ((lane < 2 * spb) && (sc[b3s].flags & 1)) {
+                const float *Es = reinterpret_cast<const float *>(
+                    reinterpret_cast<const float2 *>(regions + (size_t)b3s * sreg) + XLEN + blen);
+                float tacc = 0.0f;
+                for (int i = 0; i < nintc; i++) {
+                    const float w = reinterpret_cast<const float *>(p.pftc4[b3c])[i];
+                    tacc = __fadd_rn(tacc, __fmul_rn(Es[i], w));                          /* reference src/fsk.c:870 */
                 }
+                if (b3c) sc[b3s].tci = tacc; else sc[b3s].tcr = tacc;
             }
         }
         __syncthreads();
-        WB_CLK(5);
+        WB_CLK(3);
 
         /* ================= C: stream warps, lanes = symbols ================= */
         if (active) {
             wb_fsk_sc &c = sc[warp];
+            /* timing estimate -> resampling offsets, ppm, next nin (reference src/fsk.c:876-907): every lane of the
+               stream warp computes the same scalars, lane 0 keeps the state */
+            const float tcr = c.tcr, tci = c.tci, norm_old = c.norm, ppm_old = c.ppm;
+            const bool nan = isnan(tcr) || isnan(tci);     /* reference src/fsk.c:878-880 */
+            int nin_next = nin, low = 0, high = 0;
+            float fract = 0.0f, norm = norm_old, ppm = ppm_old, rx_timing = 0.0f;
+            if (!nan) {
+                norm = (float)((double)wb_atan2f(tci, tcr) / 6.283185307179586);
+                rx_timing = __fmul_rn(norm, (float)Pc);
+                const float dn = __fsub_rn(norm, norm_old);
+                if ((double)fabsf(dn) < .2) {
+                    const float appm = (float)(1e6 * (double)dn / (double)(float)NSYM);
+                    ppm = (float)(.9 * (double)ppm_old + .1 * (double)appm);
+                }
+                if ((double)norm > 0.25) nin_next = N_ + TS / 2;
+                else if ((double)norm < -0.25) nin_next = N_ - TS / 2;
+                else nin_next = N_;
+                low = (int)floorf(rx_timing);
+                fract = __fsub_rn(rx_timing, (float)low);
+                high = (int)ceilf(rx_timing);
+            }
+            __syncwarp();
+            if (lane == 0 && !nan) { c.norm = norm; c.ppm = ppm; c.rx_timing = rx_timing; }
             int sgw = sgc;
             asm volatile("" : "+r"(sgw));
             float *out = WB_ROW_SD(sgw) + n_out;
-            if (!(c.flags & 2)) {
-                const int low = c.low, high = c.high;
-                const float fract = c.fract, omf = __fsub_rn(1.0f, fract);
+            if (!nan) {
+                const float omf = __fsub_rn(1.0f, fract);
                 for (int i = lane; i < NSYM; i += 32) {
                     const int stt = (i + 1) * Pc;
                     const int il = wb_phys<SWZ>(stt + low), ih = wb_phys<SWZ>(stt + high);
@@ -858,11 +825,10 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 for (int i = lane; i < NBITS; i += 32)
                     out[i] = (n_out >= (unsigned)NBITS) ? out[i - NBITS] : st->sd_last[i];
             }
-            if (p.stats && !(c.flags & 2)) {
+            if (p.stats && !nan) {
                 /* Eb/N0 terms, reference src/fsk.c:985-1010: meanebno / stdebno accumulate over the symbols in order
                    (every lane repeats the 48-step sum from shuffled-in values), the log10 is left to the host */
-                const int low = c.low, high = c.high;
-                const float fract = c.fract, omf = __fsub_rn(1.0f, fract);
+                const float omf = __fsub_rn(1.0f, fract);
                 float mxv[2] = {0.0f, 0.0f};
 #pragma unroll
                 for (int rr = 0; rr < 2; rr++) {
@@ -919,12 +885,12 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                     float *l = a.frame_log + ((size_t)sg * a.log_cap + frames) * 8;
                     l[0] = (float)nin;
                     for (int m = 0; m < 4; m++) l[1 + m] = m < M ? (float)c.nb[m] : 0.0f;
-                    l[5] = c.norm; l[6] = c.ppm; l[7] = c.rx_timing;
+                    l[5] = norm; l[6] = ppm; l[7] = nan ? c.rx_timing : rx_timing;
                 }
             }
             n_out += NBITS;
             pos = pos_next;
-            nin = c.nin_next;
+            nin = nin_next;
             frames++;
             __syncwarp();
         }

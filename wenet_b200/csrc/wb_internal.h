@@ -86,7 +86,7 @@ struct wb_fsk_params {
     const float2 *back;       /* [3][Ndft/2]  phase back-off for nin = N-Ts/2, N, N+Ts/2, src/fsk.c:758 */
     /* the fine-timing oscillator again, by value: kernel parameters live in the constant bank, which is the
        right home for a table every lane reads at the same index */
-    float2 pftc[WB_MAX_NINT];
+    float4 pftc4[2][WB_MAX_NINT / 4];   /* [0] = real parts, [1] = imaginary parts, element i = ((float *)pftc4[c])[i] */
 };
 
 struct wb_stream_state {
