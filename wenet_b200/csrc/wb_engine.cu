@@ -256,6 +256,12 @@ static int upload_tables(wb_engine *e)
         hcpx d = hcexpj((float)(2 * M_PI * ((float)fp.Rs / (float)(fp.P * fp.Rs))));
         hcpx ph; ph.r = 1; ph.i = 0;
         for (int i = 0; i < fp.nint; i++) { pft[i] = ph; ((float *)fp.pftc4[0])[i] = ph.r; ((float *)fp.pftc4[1])[i] = ph.i; ph = hcmul(ph, d); }
+        /* the float recurrence falls into an exactly periodic orbit (period P) after a few steps: the blocked kernel
+           keeps one period of multipliers in registers when that holds from block WB_PFT_NT on (it does for P = 8, 10) */
+        fp.pft_steady = (fp.step == 1);
+        for (int i = (WB_PFT_NT + 1) * fp.P; i < fp.nint && fp.pft_steady; i++)
+            if (memcmp(&pft[i], &pft[i - fp.P], sizeof(hcpx)) != 0) fp.pft_steady = 0;
+        if (getenv("WB_FSK_PFT_GENERIC")) fp.pft_steady = 0;
     }
     /* per-bin tone oscillators, reference src/fsk.c:756-764, :671 */
     for (int b = 0; b < nh; b++) {

@@ -170,6 +170,12 @@ __device__ __forceinline__ float2 wb_ldg_keep2(const float2 *p)
     asm("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
     return v;
 }
+__device__ __forceinline__ float4 wb_ldg_keep4(const float4 *p)
+{
+    float4 v;
+    asm("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ float wb_ldg_keep(const float *p)
 {
     float v;
@@ -185,23 +191,77 @@ __device__ __forceinline__ int wb_phys(int n)
     return SWZ ? ((n & ~7) | ((n ^ (n >> 4)) & 7)) : n;
 }
 
-/* NB blocks of the fine-timing sum t_c += e_i * phi_ft[i] (reference src/fsk.c:870-873) for one component:
-   q_ = the blocks' e pairs (pair q of block b at b*TS/2 + (q ^ key(b))), c4 = that component of phi_ft.  The
-   multiplies are off the dependent chain of additions. */
-__device__ __forceinline__ float wb_f4c(const float4 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
-template <int TS, int NB, bool SWZ8>
-__device__ __forceinline__ float wb_b3_group(const float2 *q_, const float4 *c4, float tacc)
+/* The fine-timing sum t_c += e_i * phi_ft[i] (reference src/fsk.c:870-873) for one component, one chain per lane:
+   one dependent addition per output.  Hardly anything else runs on the warp's SM partition during this phase, so
+   nothing hides a load; left alone, ptxas issues each load a few instructions before its use and the chain waits
+   ~30 cycles per shared-memory pair (and an indexed constant-bank load issues only every ~10 cycles).  So:
+   * the e pairs travel in loop-carried registers: a rolled loop whose body adds BB blocks and refills each register
+     right after its last use with the pair BB blocks further on -- a load can sink no further than the loop's back
+     edge, one body ahead of its use;
+   * the multipliers need no loads at all in the steady state: the reference builds phi_ft by the float recurrence
+     phi_ft *= e^{j 2 pi / P}, which after a short transient falls into an exactly periodic orbit of period P = one
+     block (the host checks this on the table it built with the reference's arithmetic: p.pft_steady), so from block
+     WB_PFT_NT on every block uses the same Ts multipliers: registers.
+   q_ = e in output order (shared memory), ct = that component of phi_ft (kernel-parameter constant bank). */
+template <int TS, int NBLK_>
+__device__ __forceinline__ float wb_b3_chain(const float2 *q_, const float *ct)
 {
+    constexpr int HP = TS / 2;                  /* pairs per block */
+    constexpr int BB = 3;                       /* blocks per loop body */
+    constexpr int NP = BB * HP;                 /* pairs per body */
+    constexpr int NT = WB_PFT_NT;               /* transient blocks */
+    constexpr int NB = (NBLK_ - NT) / BB, LEFT = (NBLK_ - NT) % BB;
+    static_assert(NB >= 2, "at least two bodies");
+    float tacc = 0.0f;
+    float cs[TS];
+    float2 ev[NP];
 #pragma unroll
-    for (int b = 0; b < NB; b++) {
-        const int key = SWZ8 ? ((b >> 2) & 3) : 0;
+    for (int t = 0; t < TS; t++) cs[t] = ct[NT * TS + t];
 #pragma unroll
-        for (int q = 0; q < TS / 2; q++) {
-            const float2 ev = q_[b * (TS / 2) + (q ^ key)];
-            const int i = b * TS + 2 * q;
-            const float4 ca = c4[i >> 2], cb = c4[(i + 1) >> 2];
-            tacc = __fadd_rn(tacc, __fmul_rn(ev.x, wb_f4c(ca, i & 3)));
-            tacc = __fadd_rn(tacc, __fmul_rn(ev.y, wb_f4c(cb, (i + 1) & 3)));
+    for (int j = 0; j < NP; j++) ev[j] = q_[NT * HP + j];             /* the first body's pairs */
+    /* transient blocks: multipliers straight from the table */
+#pragma unroll
+    for (int j = 0; j < NT * HP; j++) {
+        const float2 e2 = q_[j];
+        tacc = __fadd_rn(tacc, __fmul_rn(e2.x, ct[2 * j]));
+        tacc = __fadd_rn(tacc, __fmul_rn(e2.y, ct[2 * j + 1]));
+    }
+    const float2 *qn = q_ + NT * HP + NP;       /* the next body's pairs */
+    /* one body; REFILL pairs are reloaded for the next one */
+#define WB_B3_BODY(REFILL)                                                                              \
+    do {                                                                                                \
+        _Pragma("unroll")                                                                               \
+        for (int j = 0; j < NP; j++) {                                                                  \
+            tacc = __fadd_rn(tacc, __fmul_rn(ev[j].x, cs[(2 * j) % TS]));                               \
+            tacc = __fadd_rn(tacc, __fmul_rn(ev[j].y, cs[(2 * j + 1) % TS]));                           \
+            if (j < (REFILL)) ev[j] = qn[j];                                                            \
+        }                                                                                               \
+        qn += NP;                                                                                       \
+    } while (0)
+#pragma unroll 1
+    for (int k = 0; k < NB - 1; k++) WB_B3_BODY(NP);
+    WB_B3_BODY(LEFT * HP);
+#undef WB_B3_BODY
+#pragma unroll
+    for (int j = 0; j < LEFT * HP; j++) {       /* the left-over blocks */
+        tacc = __fadd_rn(tacc, __fmul_rn(ev[j].x, cs[(2 * j) % TS]));
+        tacc = __fadd_rn(tacc, __fmul_rn(ev[j].y, cs[(2 * j + 1) % TS]));
+    }
+    return tacc;
+}
+
+/* the same without the periodicity assumption: every multiplier from the constant bank */
+template <int TS, int NBLK_>
+__device__ __forceinline__ float wb_b3_chain_generic(const float2 *q_, const float *ct)
+{
+    float tacc = 0.0f;
+#pragma unroll 1
+    for (int b = 0; b < NBLK_; b++) {
+#pragma unroll
+        for (int j = 0; j < TS / 2; j++) {
+            const float2 e2 = q_[b * (TS / 2) + j];
+            tacc = __fadd_rn(tacc, __fmul_rn(e2.x, ct[b * TS + 2 * j]));
+            tacc = __fadd_rn(tacc, __fmul_rn(e2.y, ct[b * TS + 2 * j + 1]));
         }
     }
     return tacc;
@@ -233,7 +293,6 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     constexpr int NPRE = (TS * WB_FRAME_SYMS + TS / 2 + 31) / 32;     /* lanes x NPRE >= nmax */
     constexpr bool SWZ = (TS == 8);
     constexpr int NBLK = WB_FRAME_SYMS + 1;                           /* integrator outputs come in 49 blocks of P */
-    constexpr bool B3SWZ = (TS == 8);                                 /* 4 pairs per block: XOR-swizzle the pair index */
     extern __shared__ __align__(16) unsigned char wb_fsk_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int spb = a.spb;
@@ -256,8 +315,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 #define WB_ROW_IN(SG) (a.in + (size_t)(SG) * a.in_stride)
 #define WB_ROW_SD(SG) (a.sd + (size_t)(SG) * a.sd_stride + WB_CARRY_CAP)
     const int sgc = have ? sg : 0;
-    unsigned pos = 0, fill = 0, pos0 = 0;
-    unsigned frames = 0;
+    unsigned pos = 0, fill = 0;
     int nin = N_;
     unsigned n_out = 0;
     float est[WB_NEQ];
@@ -266,7 +324,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     for (int q = 0; q < WB_NEQ; q++) est[q] = 0.0f;
     for (int i = tid; i < 3 * (Ndft >> 2); i += blockDim.x) TW[i] = __ldg(&p.tw[i]);
     if (have) {
-        pos = pos0 = (unsigned)st->in_pos; fill = (unsigned)st->in_fill; nin = st->nin;
+        pos = (unsigned)st->in_pos; fill = (unsigned)st->in_fill; nin = st->nin;
 #pragma unroll
         for (int q = 0; q < WB_NEQ; q++)
             if (lane + 32 * q < nh) est[q] = st->fft_est[lane + 32 * q];
@@ -677,12 +735,11 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                     __syncwarp();
                 }
                 if (valid) {
-                    /* E: block u = TS/2 float2 pairs at pair index (q ^ key), key = (u >> 2) & 3 for Ts = 8:
-                       conflict-free 8-byte stores here, aligned 8-byte loads in B3 */
+                    /* E in output order (8-byte stores, 4-way bank conflicts: 16 extra wavefronts per frame) so that
+                       B3 walks it with compile-time offsets */
                     float2 *eo = reinterpret_cast<float2 *>(E) + u * (TS / 2);
-                    const int key = B3SWZ ? ((u >> 2) & 3) : 0;
 #pragma unroll
-                    for (int q = 0; q < TS / 2; q++) eo[q ^ key] = make_float2(e[2 * q], e[2 * q + 1]);
+                    for (int q = 0; q < TS / 2; q++) eo[q] = make_float2(e[2 * q], e[2 * q + 1]);
                 }
             }
         } else if (active) {
@@ -738,14 +795,9 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 if (lane < spb && (sc[s].flags & 1)) {
                     const float2 *q_ = reinterpret_cast<const float2 *>(
                         reinterpret_cast<const float2 *>(regions + (size_t)s * sreg) + XLEN + blen);
-                    const float4 *c4 = p.pftc4[warp];              /* warp 0: real parts, warp 1: imaginary parts */
-                    float tacc = 0.0f;
-                    /* groups of 16 blocks (the period of the swizzle key): a loop body small enough to stay in the
-                       instruction cache -- one warp running straight-line code has nobody to hide its fetches */
-#pragma unroll 1
-                    for (int g = 0; g < NBLK / 16; g++)
-                        tacc = wb_b3_group<TS, 16, B3SWZ>(q_ + g * 16 * (TS / 2), c4 + g * 16 * TS / 4, tacc);
-                    tacc = wb_b3_group<TS, NBLK % 16, B3SWZ>(q_ + (NBLK / 16) * 16 * (TS / 2), c4 + (NBLK / 16) * 16 * TS / 4, tacc);
+                    /* warp 0: real parts, warp 1: imaginary parts of phi_ft */
+                    const float *ct = reinterpret_cast<const float *>(p.pftc4[warp]);
+                    const float tacc = p.pft_steady ? wb_b3_chain<TS, NBLK>(q_, ct) : wb_b3_chain_generic<TS, NBLK>(q_, ct);
                     if (warp == 0) sc[s].tcr = tacc; else sc[s].tci = tacc;
                 }
             }
@@ -881,8 +933,8 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             if (lane == 0) {
 #pragma unroll
                 for (int m = 0; m < M; m++) c.pb[m] = c.nb[m];              /* fsk->f_est = this frame's, :846 */
-                if (a.frame_log && frames < (unsigned)a.log_cap) {
-                    float *l = a.frame_log + ((size_t)sg * a.log_cap + frames) * 8;
+                if (a.frame_log && n_out / NBITS < (unsigned)a.log_cap) {       /* n_out / NBITS = frames so far */
+                    float *l = a.frame_log + ((size_t)sg * a.log_cap + n_out / NBITS) * 8;
                     l[0] = (float)nin;
                     for (int m = 0; m < 4; m++) l[1 + m] = m < M ? (float)c.nb[m] : 0.0f;
                     l[5] = norm; l[6] = ppm; l[7] = nan ? c.rx_timing : rx_timing;
@@ -891,7 +943,6 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             n_out += NBITS;
             pos = pos_next;
             nin = nin_next;
-            frames++;
             __syncwarp();
         }
     }
@@ -929,14 +980,15 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             }
         }
         if (lane == 0) {
+            const unsigned long long pos_start = st->in_pos;
             for (int m = 0; m < M; m++) { st->phi_c[m] = c.phi_c[m]; st->fbin[m] = c.pb[m]; }
             st->norm_rx_timing = c.norm; st->ppm = c.ppm; st->rx_timing = c.rx_timing;
-            st->nin = nin; st->frames += frames;
+            st->nin = nin; st->frames += n_out / NBITS;
             if (a.compact) { st->in_pos = dstpos; st->in_fill = a.headroom; }
             else { st->in_pos = pos; st->in_fill = fill; }
             wb_cursor &cu = a.cursor[sg];
             cu.in_fill = rem;
-            cu.consumed = (unsigned long long)(pos - pos0);
+            cu.consumed = (unsigned long long)pos - pos_start;
             cu.n_sd = n_out;
             cu.nin = nin;
         }

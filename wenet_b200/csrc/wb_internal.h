@@ -28,6 +28,7 @@
 #define WB_MAX_B1W 14
 #define WB_EYE_KEEP 96                 /* integrator outputs kept for the eye diagram: 8/M traces x 2P + offset */
 #define WB_MAX_NINT 496                /* (Nsym + 1) * P <= 49 * 10, rounded */
+#define WB_PFT_NT 2                    /* blocks of the fine-timing oscillator table before it is exactly periodic (checked by the host) */
 #define WB_FRAME_SYMS 48               /* nsyms, reference src/fsk.c:134 */
 
 #define WB_PKT_BODY_BYTES 323          /* 256 payload + 2 crc + 65 parity */
@@ -82,6 +83,7 @@ struct wb_fsk_params {
     const float2 *tw;         /* [Ndft]       kiss_fft twiddles, reference src/kiss_fft.c:357-363 */
     const uint16_t *perm;     /* [Ndft]       leaf load order of the DIT recursion */
     const float2 *pft;        /* [nint]       fine-timing oscillator, reference src/fsk.c:858-873 */
+    int pft_steady;           /* P == Ts and pft[i] == pft[i - P] for every i >= (WB_PFT_NT + 1) * P: see wb_b3_chain */
     const float2 *dphi;       /* [Ndft/2]     comp_exp_j(2 pi f/Fs), f = bin*Fs/Ndft, src/fsk.c:763 */
     const float2 *back;       /* [3][Ndft/2]  phase back-off for nin = N-Ts/2, N, N+Ts/2, src/fsk.c:758 */
     /* the fine-timing oscillator again, by value: kernel parameters live in the constant bank, which is the
