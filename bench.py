@@ -14,6 +14,10 @@ in HBM; every step demodulates a full chunk.  Multi-GPU: weak scaling, 4096 stre
 `value`  : whole-job Msamples/s with the chunk already resident in HBM (CUDA events on the engine's stream).
 `e2e`    : the same metric through the public API with HOST buffers: wb_feed_strided (pinned host -> HBM),
            wb_process, wb_sync, wb_drain_all_packets (HBM -> host) every step, wall clock around device syncs.
+           The host buffers hold the streams as cs16 -- the bytes the reference arm's `fsk_demod --cs16` reads
+           (the reference cannot read float IQ at all, src/fsk_demod.c:92-106) -- so both arms of the headline
+           ratio consume the same input; the same run with cf32 (8 B/sample over PCIe) and cu8 (2 B/sample,
+           the format of the reference's own benchmark) host buffers is reported beside it (e2e_cf32, e2e_cu8).
 `roofline`: the dominant kernel (wb_fsk_kernel): algorithmic bytes (8.5 B per IQ sample) / its
            event-timed duration, against the measured HBM peak in MEASURED_PEAKS.json.
 `cpu_baseline`: the reference's own binaries (oracle/_ref: fsk_demod | drs232_ldpc, built from the unmodified
@@ -237,7 +241,7 @@ def workload_config(args, world):
             "streams_per_gpu": args.streams, "chunk_samples": args.chunk, "in_fmt": "cf32", "framing": "v1",
             "ldpc_max_iter": 10, "parallelism": "stream-sharded x%d, no collective" % world,
             "l2": "inputs (%.1f GB per step per GPU) larger than L2" % (args.streams * args.chunk * 8 / 1e9),
-            "e2e_chunk_samples": args.e2e_chunk}
+            "e2e_in_fmt": "cs16 (the reference arm's input bytes)", "e2e_host_bytes_per_step": args.e2e_bytes}
 
 
 def main():
@@ -248,7 +252,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=4096, help="streams per GPU")
     ap.add_argument("--chunk", type=int, default=1 << 20, help="samples per stream per step (HBM-resident)")
-    ap.add_argument("--e2e-chunk", type=int, default=1 << 17, help="samples per stream per e2e step (pinned host)")
+    ap.add_argument("--e2e-bytes", type=int, default=1 << 20, help="host bytes per stream per e2e step (pinned host)")
     ap.add_argument("--sources", type=int, default=40, help="distinct synthetic streams generated on the host")
     ap.add_argument("--cpu-samples", type=int, default=32 << 20, help="samples per CPU pipe (reference arm)")
     ap.add_argument("--mode", default="v1", choices=["v1", "v2", "fsk4"],
@@ -373,9 +377,11 @@ def main():
                 "alg_bytes_per_launch": alg_bps * samples_step}
 
     # ---- e2e through the public API with host buffers ----
-    def run_e2e(fmt, ec, n_eng):
+    def run_e2e(fmt, n_eng):
         """feed (pinned host -> HBM) + process + sync + drain (HBM -> host) every step.  The streams are split over
-        n_eng engines on the same GPU so that one engine's copies overlap the other's kernels."""
+        n_eng engines on the same GPU and each engine's drain of step k is issued right before its feed of step
+        k + 1, so one engine's copies overlap the other's kernels across step boundaries too."""
+        ec = min(chunk, args.e2e_bytes // E.FMT_BPS[fmt])
         per = [n // n_eng + (1 if i < n % n_eng else 0) for i in range(n_eng)]
         elems = E.FMT_ELEMS[fmt]
         engs, pins, base = [], [], 0
@@ -389,52 +395,65 @@ def main():
                 seg = src[2 * r:2 * r + 2 * ec]
                 if fmt == "cf32":
                     pb.array[j, :] = seg
+                elif fmt == "cs16":                     # siggen.to_format: the reference divides by 1000 (FDMDV_SCALE)
+                    pb.array[j, :] = np.round(seg.astype(np.float64) * 1000.0).astype(np.int16)
                 else:                                   # the same samples as rtl_sdr would deliver them (cu8)
                     pb.array[j, :] = np.clip(np.round(seg * 127.0 + 127.0), 0, 255).astype(np.uint8)
             pins.append(pb)
             base += cnt
-        d2h = [0]
+        stat = {"d2h": 0, "samples": 0, "packets": 0}
+        pending = [False] * n_eng
+
+        def collect(i):
+            g = engs[i]
+            g.sync()
+            out = g.drain_all_packets()
+            stat["d2h"] += out.nbytes + g.n_streams * 40 + g.last_codewords * 280
+            stat["samples"] += g.last_samples
+            stat["packets"] += len(out)
+            pending[i] = False
 
         def step():
-            for g, pb in zip(engs, pins):
+            for i, (g, pb) in enumerate(zip(engs, pins)):
+                if pending[i]:
+                    collect(i)
                 g.feed_strided(pb.array)
                 g.process()
-            tot = 0
-            d2h[0] = 0
-            for g in engs:
-                g.sync()
-                out = g.drain_all_packets()
-                d2h[0] += out.nbytes + g.n_streams * 40 + g.last_codewords * 280
-                tot += g.last_samples
-            return tot
+                pending[i] = True
+
+        def flush():
+            for i in range(n_eng):
+                if pending[i]:
+                    collect(i)
 
         for _ in range(max(args.warmup, 1)):
             step()
+        flush()
         barrier()
+        stat.update(d2h=0, samples=0, packets=0)
         t0 = time.perf_counter()
-        consumed = 0
         for _ in range(args.steps):
-            consumed += step()
+            step()
+        flush()                                     # every step's results are on the host when the clock stops
         dt = time.perf_counter() - t0
         barrier()
         dt = max_over_ranks(dt)
-        consumed = sum_over_ranks(float(consumed))
+        consumed = sum_over_ranks(float(stat["samples"]))
         res = {"value": round(consumed / dt / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(n * ec * E.FMT_BPS[fmt]),
-               "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": round(1e3 * dt / args.steps, 3), "in_fmt": fmt,
-               "chunk_samples": ec, "engines": n_eng,
+               "d2h_bytes_per_step": int(stat["d2h"] // args.steps), "ms_per_step": round(1e3 * dt / args.steps, 3), "in_fmt": fmt,
+               "chunk_samples": ec, "engines": n_eng, "crc_valid_packets_per_step": stat["packets"] // args.steps,
                "api": "wb_feed_strided(pinned host) + wb_process + wb_sync + wb_drain_all_packets"}
         for g in engs:
             g.close()
         del pins
         return res
 
-    e2e = e2e_cu8 = None
+    e2e = e2e_cf32 = e2e_cu8 = None
     if not args.no_e2e:
         eng.close()
-        e2e = run_e2e("cf32", args.e2e_chunk, 2)
-        # informational: the same streams as 8-bit IQ, the format the reference's own benchmark feeds its pipe
-        # (benchmarking/README.md: csdr convert_f_u8 | fsk_demod --cu8); 4x fewer PCIe bytes per sample
-        e2e_cu8 = run_e2e("cu8", min(chunk, 4 * args.e2e_chunk), 2)
+        e2e = run_e2e("cs16", 2)
+        e2e_cf32 = run_e2e("cf32", 2)
+        e2e_cu8 = run_e2e("cu8", 2)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -446,7 +465,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world),
-            "clocks": clk, "e2e": e2e, "e2e_cu8": e2e_cu8, "gpu_launches": int(l1 - l0),
+            "clocks": clk, "e2e": e2e, "e2e_cf32": e2e_cf32, "e2e_cu8": e2e_cu8, "gpu_launches": int(l1 - l0),
             "roofline": roofline, "cpu_baseline": cpu,
             "work_per_step_per_gpu": {"samples": int(samples_step), "codewords": int(codewords_step),
                                       "crc_valid_packets": packets_last},

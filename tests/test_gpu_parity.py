@@ -220,6 +220,24 @@ def test_4fsk_soft_vs_oracle(eng_mod, oracle_port):
     e.close()
 
 
+def test_fine_timing_generic_path_vs_oracle(eng_mod, oracle_port, monkeypatch):
+    """the fine-timing chain without the periodic-table shortcut (what wb_create selects when the host finds the
+    reference's phi_ft recurrence not periodic) gives the same soft decisions and nin sequence"""
+    cfg = siggen.V1
+    raw, _ = siggen.make_stream(11, n_packets=2, ebno_db=7.0, fmt="cf32", clock_ppm=1800.0)
+    sd_o, log_o, _, _ = _run_oracle_stream(oracle_port, raw, "cf32", cfg["Fs"], cfg["Rs"], 2, None)
+    monkeypatch.setenv("WB_FSK_PFT_GENERIC", "1")
+    e = eng_mod.Engine(1, in_fmt="cf32", framing="none", chunk_samples=raw.size // 2 + 1024)
+    monkeypatch.delenv("WB_FSK_PFT_GENERIC")
+    e.enable_frame_log(len(log_o) + 4)
+    e.feed([raw])
+    e.process()
+    e.sync()
+    assert np.array_equal(e.drain_soft(0).view(np.uint32), sd_o.view(np.uint32))
+    assert np.array_equal(e.read_frame_log(0, len(log_o))[:, 0], log_o[:, 0]), "nin sequence"
+    e.close()
+
+
 def test_many_streams_one_launch(eng_mod, oracle_port):
     """more streams than one CTA holds, ragged lengths, some empty: every stream still matches"""
     cfg = siggen.V1

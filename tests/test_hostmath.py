@@ -63,3 +63,18 @@ def test_phi0_tables(hm, oracle_port):
         got = _call(getattr(hm, name), x, out_dtype=np.float32)
         assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), name
     assert math.isclose(float(oracle_port.phi0(np.float32([0.5]))[0]), 1.5735153, rel_tol=1e-7)
+
+
+@pytest.mark.parametrize("P,Rs", [(8, 115177), (10, 96000)])
+def test_fine_timing_oscillator_is_periodic(hm, P, Rs):
+    """the reference's float recurrence for phi_ft (src/fsk.c:858-873) falls into an exactly periodic orbit of period P
+    within two symbols: wb_fsk_kernel keeps one period of multipliers in registers from block WB_PFT_NT = 2 on
+    (wb_create re-checks this on the table it builds and falls back to the table walk otherwise)"""
+    n = 49 * P
+    re, im = np.empty(n, np.float32), np.empty(n, np.float32)
+    hm.wbh_pft_table(C.c_int(P), C.c_int(Rs), C.c_int(n), re.ctypes.data_as(C.c_void_p), im.ctypes.data_as(C.c_void_p))
+    assert re[0] == 1.0 and im[0] == 0.0
+    nt = 2
+    assert np.array_equal(re[(nt + 1) * P:].view(np.uint32), re[nt * P:-P].view(np.uint32))
+    assert np.array_equal(im[(nt + 1) * P:].view(np.uint32), im[nt * P:-P].view(np.uint32))
+    assert not np.array_equal(re[P:2 * P].view(np.uint32), re[:P].view(np.uint32))      # the transient is real

@@ -483,7 +483,7 @@ extern "C" int wb_create(const wb_config *cfg, wb_engine **out)
         {
             int W = std::min(spb, 4);
             if (getenv("WB_FSK_B1W")) W = std::max(1, std::min(std::min(spb, WB_MAX_B1W), atoi(getenv("WB_FSK_B1W"))));
-            double r = getenv("WB_FSK_B1R") ? atof(getenv("WB_FSK_B1R")) : 0.75;
+            double r = getenv("WB_FSK_B1R") ? atof(getenv("WB_FSK_B1R")) : 0.7;
             const int nsteps = e->fp.nsteps;
             double tot = 0, wgt = 1;
             for (int j = 0; j < W; j++) { tot += wgt; wgt *= r; }

@@ -64,3 +64,17 @@ long wbh_phi0_pairs(const float *x, float *out, long n)
     for (i = 0; i < n; i++) out[i] = wb_phi0_eval_pairs(&t, x[i]);
     return 0;
 }
+
+/* fine-timing oscillator table as wb_engine.cu: upload_tables builds it (reference src/fsk.c:858-873: phi_ft starts
+   at 1 and is multiplied by comp_exp_j(2 pi Rs/(P Rs)) after every use, float arithmetic, never normalised) */
+#include <math.h>
+void wbh_pft_table(int P, int Rs, int n, float *re, float *im)
+{
+    float a = (float)(2 * M_PI * ((float)Rs / (float)(P * Rs)));
+    float dr = cosf(a), di = sinf(a), pr = 1.0f, pi_ = 0.0f;
+    for (int i = 0; i < n; i++) {
+        re[i] = pr; im[i] = pi_;
+        float nr = pr * dr - pi_ * di, ni = pr * di + pi_ * dr;     /* cmult, src/comp_prim.h (no FMA: -ffp-contract=off) */
+        pr = nr; pi_ = ni;
+    }
+}
