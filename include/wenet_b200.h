@@ -142,9 +142,36 @@ int  wb_ldpc_decode_batch(wb_engine *e, const float *llr, size_t n, int max_iter
 /* sd_to_llr() (src/mpdecode_core.h:39) over n blocks of 2580 float soft decisions */
 int  wb_sd_to_llr_batch(wb_engine *e, const float *sd, size_t n, float *llr);
 
+/* ---- transmit side on the device (synthetic input in HBM) ---------------- */
+/* What the receive path decodes, built where wb_feed would have put it: for every stream n_packets frames
+   (reference tx/PacketTX.py:123-137 frame_packet: payload + CRC16 + RA-LDPC parity of tx/ldpc_encoder.py /
+   src/mpdecode_core.c:72-91, preamble + unique word, v1 UART framing or v2 scrambling per the engine's framing),
+   idle '1' bits around them, modulated by the reference's fsk_mod_c (src/fsk.c:1162-1204; without noise the samples
+   are bit-identical to it, amplitude 2) and, if ebno_db is finite, AWGN + peak normalisation as
+   benchmarking/generate_lowsnr.py:70-89 (unit-amplitude signal, max |y| = 1).  With framing NONE the payload bytes
+   are sent as they are, MSB first (M = 4: two bits per symbol).  The bit stream is padded with idle bits to whole
+   modulator calls of 48 symbols.  Equivalent to a wb_feed of *nsamp_per_stream samples to every stream. */
+typedef struct wb_tx_config {
+    uint32_t struct_size;      /* sizeof(wb_tx_config) */
+    int32_t  n_packets;        /* frames (framing NONE: 256-byte blocks) per stream */
+    int32_t  lead_in_bits;     /* idle bits before the first frame */
+    int32_t  gap_bits;         /* idle bits after every frame */
+    int32_t  tail_bits;        /* idle bits at the end */
+    int32_t  f1_tx, fs_tx;     /* Hz: tone of symbol 0 and tone spacing (tx_f1 / tx_fs of fsk_create_hbr, src/fsk.h:110) */
+    float    ebno_db;          /* AWGN at this Eb/N0; NaN = none (the reference modulator's output as it is) */
+    uint64_t seed;             /* noise generator seed */
+} wb_tx_config;
+/* payloads: host memory, [n_streams][n_packets][256] bytes */
+int  wb_tx_synthesize(wb_engine *e, const uint8_t *payloads, const wb_tx_config *cfg, uint64_t *nsamp_per_stream);
+/* test tap: the on-air bits (one byte each) of a stream built by the last wb_tx_synthesize */
+int  wb_tx_read_bits(wb_engine *e, int stream, uint8_t *bits, size_t cap, size_t *n);
+
 /* ---- HBM-resident benchmarking helpers --------------------------------- */
 /* device address / stride / capacity of the resident input buffer */
 int  wb_dev_input(wb_engine *e, void **dptr, uint64_t *stride_bytes, uint64_t *capacity_samples);
+/* test tap: samples [first, first + nsamp) of a stream's resident input row (counted from the headroom mark, where a
+   fresh engine's first wb_feed / wb_tx_synthesize lands), in the engine's input format */
+int  wb_dev_read_input(wb_engine *e, int stream, uint64_t first, uint64_t nsamp, void *out);
 /* declare nsamp samples resident in every stream and rewind the read positions to 0 */
 int  wb_dev_set_fill(wb_engine *e, uint64_t nsamp);
 /* replicate stream 0..n_src-1 of the resident input into all streams, stream s = source (s % n_src)

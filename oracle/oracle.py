@@ -126,6 +126,32 @@ class Oracle:
         d = np.frombuffer(bytes(data), dtype=np.uint8)
         return int(self.lib.wo_crc16(_p(d), d.size))
 
+    # ---- transmit side ----
+    def tx_frame_bits(self, payload, framing="v1"):
+        """one on-air frame as 0/1 bytes (reference tx/PacketTX.py:123-137 + UART / scramble)"""
+        assert self.kind == "port"
+        bits = np.zeros(4096, dtype=np.uint8)
+        pl = np.frombuffer(bytes(payload), dtype=np.uint8)
+        self.lib.wo_tx_frame_bits.restype = C.c_int
+        n = self.lib.wo_tx_frame_bits(_p(pl), C.c_int(pl.size), C.c_int(1 if framing == "v1" else 2), _p(bits))
+        return bits[:n].copy()
+
+    def fsk_mod(self, bits, Fs, Rs, f1_tx, fs_tx, M=2):
+        """fsk_mod_c (reference src/fsk.c:1162-1204) call after call over `bits` (a multiple of Nbits) -> cf32"""
+        pre, L = self.pre, self.lib
+        h = C.c_void_p(getattr(L, pre + "fsk_create")(Fs, Rs, Fs // Rs, M))
+        getattr(L, pre + "fsk_set_tx")(h, C.c_int(f1_tx), C.c_int(fs_tx))
+        nbits = getattr(L, pre + "fsk_nbits")(h)
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        assert bits.size % nbits == 0
+        ncall = bits.size // nbits
+        ns = 48 * (Fs // Rs)
+        out = np.zeros((ncall, 2 * ns), dtype=np.float32)
+        for k in range(ncall):
+            getattr(L, pre + "fsk_mod_c")(h, _p(out[k]), _p(bits[k * nbits:(k + 1) * nbits]))
+        getattr(L, pre + "fsk_destroy")(h)
+        return out.reshape(-1)
+
     # ---- FSK ----
     def fsk(self, Fs, Rs, M=2, P=None):
         return _Fsk(self, Fs, Rs, M, P if P else Fs // Rs)

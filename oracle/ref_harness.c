@@ -232,3 +232,16 @@ long ref_fsk_run(void *h, int fmt, const void *raw, long nsamp,
     *consumed = pos;
     return frames;
 }
+
+/* ---- transmit side: the reference's own modulator (src/fsk.c:1162-1204) ---- */
+void ref_fsk_set_tx(void *h, int f1_tx, int fs_tx)
+{
+    struct FSK *f = (struct FSK *)h;
+    f->f1_tx = f1_tx; f->fs_tx = fs_tx;          /* what fsk_create_hbr stores from its tx_f1 / tx_fs arguments, src/fsk.c:161-162 */
+    f->tx_phase_c.real = cosf(0); f->tx_phase_c.imag = sinf(0);     /* comp_exp_j(0), src/fsk.c:237 */
+}
+void ref_fsk_mod_c(void *h, float *out, const uint8_t *tx_bits)
+{
+    fsk_mod_c((struct FSK *)h, (COMP *)out, (uint8_t *)tx_bits);
+}
+

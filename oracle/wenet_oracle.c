@@ -377,6 +377,9 @@ struct wo_fsk {
     float rx_eye[EYE_TR][EYE_IND];
     /* scratch */
     cpx *fin, *fout, *f_int[MAXM];
+    /* modulator, reference struct FSK f1_tx / fs_tx / tx_phase_c */
+    int f1_tx, fs_tx;
+    cpx tx_phase_c;
 };
 
 /* kiss_fft factorisation, reference src/kiss_fft.c:309-330 */
@@ -784,3 +787,85 @@ long wo_fsk_run(wo_fsk *f, int fmt, const void *raw, long nsamp,
     *n_sd = nsd; *consumed = pos;
     return frames;
 }
+
+/* ===================================================================== */
+/* Transmit side: what the receive path above decodes.   */
+/* ===================================================================== */
+
+/* One on-air frame as 0/1 bytes in transmit order.
+ *   reference tx/PacketTX.py:123-137 (frame_packet): payload padded with 0x55 to 256 bytes, CRC16 little endian,
+ *     parity = ldpc_encode(payload + crc) packed MSB first into 65 bytes (tx/ldpc_encoder.py:42-52),
+ *     preamble (16 x 0x55, tx/PacketTX.py:65) + unique word AB CD EF 01 (:66) + scramble(body);
+ *   mode 1 (RS232): no scrambling (tx/radio_wrappers.py:502-503); the UART sends every byte as start 0, 8 data bits
+ *     LSB first, stop 1 -- the framing src/drs232_ldpc.c:211-225 undoes;
+ *   mode 2: body XORed with the 125-byte table of tx/radio_wrappers.py:385-404 (= the signs of
+ *     src/wenet_scramble.h:22 packed MSB first), bits MSB first (tx/radio_wrappers.py:410-417).
+ * bits must hold 3430 (mode 1) / 2744 (mode 2) bytes; returns the count. */
+int wo_tx_frame_bits(const uint8_t *payload, int payload_len, int mode, uint8_t *bits)
+{
+    static const uint8_t head[20] = {0x55, 0x55, 0x55, 0x55, 0x55, 0x55, 0x55, 0x55, 0x55, 0x55, 0x55, 0x55, 0x55, 0x55, 0x55, 0x55,
+                                     0xAB, 0xCD, 0xEF, 0x01};
+    uint8_t raw[20 + FRAME_BYTES], ib[WB_NDATA], pb[WB_NPAR + 4];
+    uint16_t crc;
+    int i, k, n = 0;
+    memcpy(raw, head, 20);
+    for (i = 0; i < PKT_BYTES; i++) raw[20 + i] = (i < payload_len) ? payload[i] : 0x55;
+    crc = wo_crc16(raw + 20, PKT_BYTES);
+    raw[20 + PKT_BYTES] = (uint8_t)(crc & 0xFF);               /* struct.pack("<H", crc) */
+    raw[20 + PKT_BYTES + 1] = (uint8_t)(crc >> 8);
+    for (i = 0; i < WB_NDATA; i++) ib[i] = (raw[20 + i / 8] >> (7 - i % 8)) & 1;   /* np.unpackbits: MSB first */
+    wo_ldpc_encode(ib, pb);
+    for (i = 0; i < 4; i++) pb[WB_NPAR + i] = 0;                /* np.packbits pads with zeros */
+    for (i = 0; i < 65; i++) {
+        uint8_t b = 0;
+        for (k = 0; k < 8; k++) b = (uint8_t)((b << 1) | pb[8 * i + k]);
+        raw[20 + PKT_BYTES + 2 + i] = b;
+    }
+    if (mode == 2) {
+        for (i = 0; i < FRAME_BYTES; i++) {
+            uint8_t sc = 0;
+            for (k = 0; k < 8; k++) sc = (uint8_t)((sc << 1) | wb_scramble_neg[(8 * (i % 125) + k) % WB_SCRAMBLE_LEN]);
+            raw[20 + i] ^= sc;
+        }
+        for (i = 0; i < 20 + FRAME_BYTES; i++)
+            for (k = 7; k >= 0; k--) bits[n++] = (raw[i] >> k) & 1;
+    } else {
+        for (i = 0; i < 20 + FRAME_BYTES; i++) {
+            bits[n++] = 0;
+            for (k = 0; k < 8; k++) bits[n++] = (raw[i] >> k) & 1;
+            bits[n++] = 1;
+        }
+    }
+    return n;
+}
+
+/* reference src/fsk.c:1162-1204 (fsk_mod_c): Nsym symbols -> Nsym*Ts complex samples of amplitude 2; the phase
+ * carries over between calls (fsk->tx_phase_c, normalised at the end of every call).  tx_bits holds Nbits 0/1 bytes. */
+void wo_fsk_mod_c(wo_fsk *f, float *out, const uint8_t *tx_bits)
+{
+    cpx ph = f->tx_phase_c, dosc[MAXM];
+    int m, i, j, bit_i = 0;
+    for (m = 0; m < f->M; m++)
+        dosc[m] = cexpj((float)(2 * M_PI * ((float)(f->f1_tx + (f->fs_tx * m)) / (float)(f->Fs))));
+    for (i = 0; i < f->Nsym; i++) {
+        int sym = 0;
+        for (m = f->M; m >>= 1;) { sym = (sym << 1) | (tx_bits[bit_i] == 1 ? 1 : 0); bit_i++; }
+        for (j = 0; j < f->Ts; j++) {
+            ph = cmul(ph, dosc[sym]);
+            out[2 * (i * f->Ts + j)] = 2 * ph.r;                /* fcmult(2, tx_phase_c) */
+            out[2 * (i * f->Ts + j) + 1] = 2 * ph.i;
+        }
+    }
+    {   /* comp_normalize, src/comp_prim.h:133-139 */
+        float av = sqrtf(ph.r * ph.r + ph.i * ph.i);
+        ph.r = ph.r / av; ph.i = ph.i / av;
+    }
+    f->tx_phase_c = ph;
+}
+
+void wo_fsk_set_tx(wo_fsk *f, int f1_tx, int fs_tx)
+{
+    f->f1_tx = f1_tx; f->fs_tx = fs_tx;
+    f->tx_phase_c.r = 1.0f; f->tx_phase_c.i = 0.0f;             /* comp_exp_j(0), src/fsk.c:237 */
+}
+

@@ -81,6 +81,14 @@ long wo_fsk_run(wo_fsk *f, int fmt, const void *raw, long nsamp,
                 float *sd_out, long sd_cap, long *n_sd,
                 float *frame_log, long log_cap, long *consumed);
 
+/* ---- transmit side ---- */
+/* one on-air frame (preamble + unique word + body) as 0/1 bytes in transmit order: reference tx/PacketTX.py:123-137,
+ * tx/radio_wrappers.py:385-417 / :502-559; mode 1 = RS232 (3430 bits), 2 = scrambled v2 (2744 bits) */
+int wo_tx_frame_bits(const uint8_t *payload, int payload_len, int mode, uint8_t *bits);
+/* reference src/fsk.c:1162-1204 (fsk_mod_c); wo_fsk_set_tx = the tx_f1 / tx_fs arguments of fsk_create_hbr */
+void wo_fsk_set_tx(wo_fsk *f, int f1_tx, int fs_tx);
+void wo_fsk_mod_c(wo_fsk *f, float *out, const uint8_t *tx_bits);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,3 +69,18 @@ def test_fsk_4fsk_stream(oracle_port):
     # the demodulator output lags the transmitted symbols by a constant few symbols: find it
     best = max(np.mean(hard[lag:n] == z["symbols"][:n - lag]) for lag in range(0, 6))
     assert best > 0.99
+
+
+def test_tx_side(oracle_port):
+    """transmit side: the modulator restatement against the reference's fsk_mod_c output, the frame
+    builder against frames the reference receiver accepted, the scramble table against tx/radio_wrappers.py's"""
+    g = np.load(os.path.join(GOLD, "tx.npz"))
+    assert np.array_equal(oracle_port.fsk_mod(g["bits2"], 921416, 115177, 129763, 143594, M=2).view(np.uint32),
+                          g["mod2"].view(np.uint32))
+    assert np.array_equal(oracle_port.fsk_mod(g["bits4"], 921416, 115177, 46071, 115177, M=4).view(np.uint32),
+                          g["mod4"].view(np.uint32))
+    for k, pl in enumerate(g["payloads"]):
+        assert np.array_equal(oracle_port.tx_frame_bits(pl.tobytes(), "v1"), g["frames_v1"][k])
+        assert np.array_equal(oracle_port.tx_frame_bits(pl.tobytes(), "v2"), g["frames_v2"][k])
+    from wenet_b200 import siggen
+    assert np.array_equal(siggen.scramble_bytes(), g["scramble"])

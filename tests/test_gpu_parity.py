@@ -365,3 +365,97 @@ def test_stats_surface(eng_mod, oracle_port):
     if so[16] >= -1.0:            # high_sample + 1 >= 0: the reference's indices stay inside f_int
         assert np.allclose(eye_g, eye_o, rtol=0, atol=1e-6)
     e.close()
+
+
+# ---- transmit side on the device ----
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("framing", ["v1", "v2"])
+def test_tx_frames_and_modulator_vs_oracle(eng_mod, oracle_port, framing):
+    """wb_tx_synthesize without noise: the on-air bits equal the TX restatement's (which the reference receiver accepts)
+    and the samples equal the reference modulator's arithmetic bit for bit; then the engine decodes its own signal"""
+    cfg = siggen.V1 if framing == "v1" else siggen.V2
+    n, npk = 5, 3
+    rng = np.random.default_rng(21)
+    pl = rng.integers(0, 256, size=(n, npk, 256), dtype=np.uint8)
+    f1, fs = int(cfg["f_lo"]), int(cfg["f_hi"] - cfg["f_lo"])
+    e = eng_mod.Engine(n, Fs=cfg["Fs"], Rs=cfg["Rs"], in_fmt="cf32", framing=framing, chunk_samples=200000)
+    ns = e.tx_synthesize(pl, f1, fs, ebno_db=None, lead_in=2000, gap=24, tail=400)
+    for s in range(n):
+        parts = [np.ones(2000, np.uint8)]
+        for k in range(npk):
+            parts += [oracle_port.tx_frame_bits(pl[s, k].tobytes(), framing), np.ones(24, np.uint8)]
+        bits = np.concatenate(parts + [np.ones(400, np.uint8)])
+        bits = np.concatenate([bits, np.ones((-bits.size) % 48, np.uint8)])
+        assert np.array_equal(e.tx_read_bits(s), bits), s
+        x = oracle_port.fsk_mod(bits, cfg["Fs"], cfg["Rs"], f1, fs)
+        assert ns * 2 == x.size
+        y = e.dev_read_input(s, ns)
+        assert np.array_equal(y.view(np.uint32), x.view(np.uint32)), s
+    e.process()
+    e.sync()
+    for s in range(n):
+        assert e.drain_packets(s) == pl[s].tobytes(), s
+    e.close()
+
+
+@pytest.mark.gpu
+def test_tx_golden_modulator(eng_mod):
+    """the device modulator against the reference's own fsk_mod_c output (tests/golden/tx.npz), 2-FSK and 4-FSK"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tx.npz"))
+    for M, bits, mod, f1, fs in ((2, g["bits2"], g["mod2"], 129763, 143594), (4, g["bits4"], g["mod4"], 46071, 115177)):
+        nblk = bits.size // 2048 + 1
+        pad = np.concatenate([bits, np.ones(nblk * 2048 - bits.size, np.uint8)])
+        pl = np.packbits(pad).reshape(1, nblk, 256)
+        e = eng_mod.Engine(1, M=M, in_fmt="cf32", framing="none", chunk_samples=100000)
+        ns = e.tx_synthesize(pl, f1, fs, ebno_db=None, lead_in=0, gap=0, tail=0)
+        y = e.dev_read_input(0, ns)
+        assert np.array_equal(y[:mod.size].view(np.uint32), mod.view(np.uint32)), M
+        e.close()
+
+
+@pytest.mark.gpu
+def test_tx_noisy_round_trip(eng_mod, oracle_port):
+    """AWGN + peak normalisation on the device (benchmarking/generate_lowsnr.py): 10 dB streams decode completely,
+    4 dB streams do not; the oracle demodulates the very same samples to the very same soft decisions; other input
+    formats are converted on the device"""
+    cfg = siggen.V1
+    n, npk = 6, 4
+    rng = np.random.default_rng(22)
+    pl = rng.integers(0, 256, size=(n, npk, 256), dtype=np.uint8)
+    f1, fs = int(cfg["f_lo"]), int(cfg["f_hi"] - cfg["f_lo"])
+    e = eng_mod.Engine(n, in_fmt="cf32", framing="v1", chunk_samples=200000)
+    ns = e.tx_synthesize(pl, f1, fs, ebno_db=10.0, seed=5)
+    ys = [e.dev_read_input(s, ns) for s in range(n)]
+    for s in range(n):
+        m = np.abs(ys[s].view(np.complex64))
+        assert abs(m.max() - 1.0) < 1e-6                               # peak normalised
+        if s:
+            assert not np.array_equal(ys[s], ys[0])
+    # noise level: the unit-amplitude signal sits at 1/peak, noise variance Ts/EbN0 relative to it
+    x = ys[0].view(np.complex64).astype(np.complex128)
+    pw = np.mean(np.abs(x) ** 2)
+    g = 1.0 / (pw / (1.0 + 8.0 / 10.0)) ** 0.5                         # = peak, from E|y|^2 = (1 + nvar) / peak^2
+    assert 2.0 < g < 6.0
+    e.process()
+    e.sync()
+    for s in range(n):
+        assert e.drain_packets(s) == pl[s].tobytes(), s
+        sd_o, _, _, res_o = _run_oracle_stream(oracle_port, ys[s], "cf32", cfg["Fs"], cfg["Rs"], 2, "v1")
+        assert res_o["packets"] == pl[s].tobytes()
+    e.close()
+    e = eng_mod.Engine(n, in_fmt="cf32", framing="v1", chunk_samples=200000)
+    e.tx_synthesize(pl, f1, fs, ebno_db=4.0, seed=6)
+    e.process()
+    e.sync()
+    assert sum(len(e.drain_packets(s)) for s in range(n)) < n * npk * 256 // 4
+    e.close()
+    for fmt in ("cs16", "cu8"):
+        e = eng_mod.Engine(n, in_fmt=fmt, framing="v1", chunk_samples=200000)
+        e.tx_synthesize(pl, f1, fs, ebno_db=12.0, seed=7)
+        e.process()
+        e.sync()
+        for s in range(n):
+            assert e.drain_packets(s) == pl[s].tobytes(), (fmt, s)
+        e.close()

@@ -91,3 +91,39 @@ def test_full_pipe_vs_cli(oracle_port, oracle_ref):
     sd, _, _ = oracle_port.fsk(921416, 115177).run(raw, "cs16")
     out = oracle_port.deframer("v1", 10).feed(sd)["packets"]
     assert out == O.run_ref_pipe(raw.tobytes(), fmt="cs16") == b"".join(payloads)
+
+
+# ---- transmit side ----
+
+@pytest.mark.parametrize("M,f1,fs", [(2, 129763, 143594), (4, 46071, 115177)])
+def test_tx_modulator(oracle_port, oracle_ref, M, f1, fs):
+    """wo_fsk_mod_c == the reference's fsk_mod_c (src/fsk.c:1162-1204), call after call (the phase carries over)"""
+    rng = np.random.default_rng(40 + M)
+    nbits = 48 * (1 if M == 2 else 2)
+    bits = rng.integers(0, 2, nbits * 7).astype(np.uint8)
+    a = oracle_port.fsk_mod(bits, 921416, 115177, f1, fs, M=M)
+    b = oracle_ref.fsk_mod(bits, 921416, 115177, f1, fs, M=M)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert abs(np.abs(a.view(np.complex64)).mean() - 2.0) < 1e-3          # fcmult(2, tx_phase_c)
+
+
+@pytest.mark.parametrize("framing", ["v1", "v2"])
+def test_tx_frames_decode_in_the_reference_receiver(oracle_port, oracle_ref, framing):
+    """frames from the TX restatement, modulated by the reference's own fsk_mod_c, come back out of the unmodified
+    reference receiver (fsk_demod | drs232_ldpc / wenet_ldpc): pins bit order, UART framing / scrambling, CRC
+    endianness and parity packing of wo_tx_frame_bits against the code that has to undo them"""
+    from oracle import oracle as O
+    cfg = siggen.V1 if framing == "v1" else siggen.V2
+    rng = np.random.default_rng(7)
+    payloads = siggen.random_payloads(rng, 3)
+    bits = [np.ones(2000, np.uint8)] + [oracle_port.tx_frame_bits(p, framing) for p in payloads] + [np.ones(400, np.uint8)]
+    bits = np.concatenate(bits)
+    bits = np.concatenate([bits, np.ones((-bits.size) % 48, np.uint8)])
+    f1, fs = int(cfg["f_lo"]), int(cfg["f_hi"] - cfg["f_lo"])
+    x = oracle_ref.fsk_mod(bits, cfg["Fs"], cfg["Rs"], f1, fs)
+    cs16 = np.round(x.astype(np.float64) * 500.0).astype(np.int16)         # amplitude 2 -> 1000 = unit after /FDMDV_SCALE
+    out = O.run_ref_pipe(cs16.tobytes(), "cs16", Fs=cfg["Fs"], Rs=cfg["Rs"], framing=framing)
+    assert out == b"".join(payloads)
+    # and the numpy signal generator the other tests use builds the same frames
+    for p in payloads:
+        assert np.array_equal(oracle_port.tx_frame_bits(p, framing), siggen.frame_bits(p, framing))

@@ -11,6 +11,10 @@ The outputs are committed; tests never read /root/reference.
   ldpc_llr.npz  soft-decision blocks -> reference sd_to_llr() LLRs -> run_ldpc_decoder() bits / iterations / parity
                 counts for max_iter 10 and 100
   phi0.npz      arguments around every breakpoint (+ specials) -> reference phi0()
+  tx.npz        transmit side: bit patterns -> the reference's fsk_mod_c samples (2-FSK at the v1
+                tones, 4-FSK); three payloads and their v1 / v2 on-air frame bits, accepted by the reference receiver
+                (this script checks that fsk_mod_c of those frames | fsk_demod | drs232_ldpc / wenet_ldpc returns
+                the payloads before it writes them); the v2 scramble table as tx/radio_wrappers.py:386-398 lists it
 """
 import os
 import subprocess
@@ -86,6 +90,33 @@ def main():
         xs += [np.nextafter(v, np.float32(-np.inf)), v, np.nextafter(v, np.float32(np.inf))]
     x = np.array(xs, dtype=np.float32)
     np.savez_compressed(os.path.join(GOLD, "phi0.npz"), x=x, y=ref.phi0(x))
+
+    # ---- transmit side ----
+    import re
+    port = O.Oracle("port")
+    rng = np.random.default_rng(77)
+    bits2 = rng.integers(0, 2, 48 * 6).astype(np.uint8)
+    bits4 = rng.integers(0, 2, 96 * 4).astype(np.uint8)
+    mod2 = ref.fsk_mod(bits2, 921416, 115177, 129763, 143594, M=2)
+    mod4 = ref.fsk_mod(bits4, 921416, 115177, 46071, 115177, M=4)
+    payloads = siggen.random_payloads(rng, 3)
+    frames = {}
+    for framing, cfg in (("v1", siggen.V1), ("v2", siggen.V2)):
+        fb = [port.tx_frame_bits(p, framing) for p in payloads]
+        allb = np.concatenate([np.ones(2000, np.uint8)] + fb + [np.ones(400, np.uint8)])
+        allb = np.concatenate([allb, np.ones((-allb.size) % 48, np.uint8)])
+        x = ref.fsk_mod(allb, cfg["Fs"], cfg["Rs"], int(cfg["f_lo"]), int(cfg["f_hi"] - cfg["f_lo"]))
+        out = O.run_ref_pipe(np.round(x.astype(np.float64) * 500.0).astype(np.int16).tobytes(), "cs16", Fs=cfg["Fs"], Rs=cfg["Rs"],
+                             framing=framing)
+        assert out == b"".join(payloads), "the reference receiver does not accept the %s frames" % framing
+        frames[framing] = np.stack(fb)
+    src = open("/root/reference/tx/radio_wrappers.py").read()
+    m = re.search(r"class RFM98W_I2S.*?scramble_code = \[(.*?)\]", src, re.S)
+    scramble = np.array([int(t, 16) for t in re.findall(r"0x[0-9a-fA-F]+", m.group(1))], dtype=np.uint8)
+    assert scramble.size == 125
+    np.savez_compressed(os.path.join(GOLD, "tx.npz"), bits2=bits2, mod2=mod2, bits4=bits4, mod4=mod4,
+                        payloads=np.stack([np.frombuffer(p, np.uint8) for p in payloads]), frames_v1=frames["v1"],
+                        frames_v2=frames["v2"], scramble=scramble)
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

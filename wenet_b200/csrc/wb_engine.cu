@@ -27,6 +27,7 @@
 #include "wb_fsk_kernel.cuh"
 #include "wb_deframe_kernel.cuh"
 #include "wb_ldpc_kernel.cuh"
+#include "wb_tx_kernel.cuh"
 
 #define WB_HEADROOM 512u    /* samples in front of every input row for the parked remainder (>= WB_MAX_NIN) */
 
@@ -97,6 +98,9 @@ struct wb_engine {
     bool uniform_fill;                             /* every stream has the same fill (strided feed possible) */
     bool pending;                                  /* a wb_process has not been collected yet */
     bool resident_mode;                            /* wb_dev_set_fill: do not compact */
+    uint8_t *d_tx_bits;                            /* wb_tx_synthesize: on-air bits, one byte each */
+    unsigned long long tx_bits_stride, tx_nbits;
+    uint16_t *d_hrows;
     uint64_t launches;
     uint64_t last_codewords, last_samples;
     float kernel_ms[4];
@@ -330,6 +334,7 @@ extern "C" void wb_destroy(wb_engine *e)
     cudaFree(e->d_c4); cudaFree(e->d_cw); cudaFree(e->d_cw_packed); cudaFree(e->d_llr); cudaFree(e->d_llr_packed);
     cudaFree(e->d_gather); cudaFree(e->d_fill); cudaFree(e->d_frame_log); cudaFree(e->d_tables); cudaFree(e->d_vedge);
     cudaFree(e->d_crc_tab); cudaFree(e->d_scramble); cudaFree(e->d_lut);
+    cudaFree(e->d_tx_bits); cudaFree(e->d_hrows);
     cudaFree(e->d_bench_llr); cudaFree(e->d_bench_bits); cudaFree(e->d_bench_iters); cudaFree(e->d_bench_pcc);
     for (int i = 0; i < 8; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     if (e->tev0) cudaEventDestroy(e->tev0);
@@ -399,6 +404,7 @@ extern "C" int wb_create(const wb_config *cfg, wb_engine **out)
     for (int i = 0; i < 8; i++) e->ev[i] = nullptr;
     e->d_in = nullptr; e->d_state = nullptr; e->d_cursor = nullptr; e->d_sd = nullptr; e->d_jobs = nullptr; e->d_c4 = nullptr;
     e->d_cw = e->d_cw_packed = nullptr; e->d_llr = e->d_llr_packed = nullptr; e->d_gather = nullptr; e->d_fill = nullptr; e->d_frame_log = nullptr;
+    e->d_tx_bits = nullptr; e->d_hrows = nullptr; e->tx_bits_stride = e->tx_nbits = 0;
     e->d_tables = nullptr; e->d_vedge = nullptr; e->d_crc_tab = nullptr; e->d_scramble = nullptr; e->d_lut = nullptr;
     e->d_bench_llr = nullptr; e->d_bench_bits = nullptr; e->d_bench_iters = e->d_bench_pcc = nullptr; e->bench_n = 0;
     e->launches = 0; e->last_codewords = e->last_samples = 0; e->log_cap = 0;
@@ -1214,6 +1220,124 @@ extern "C" int wb_geometry(wb_engine *e, int32_t *out, int n)
     int32_t g[14] = {e->fp.N, e->fp.Nbits, e->fp.Ts, e->fp.P, e->fp.Ndft, e->fp.nmax, e->job_cap, (int32_t)e->sd_cap,
                      e->fp.Nsym, e->fp.M, e->max_iter, e->dp.nsym, e->spb, (int32_t)e->fsk_smem};
     for (int i = 0; i < n && i < 14; i++) out[i] = g[i];
+    return WB_OK;
+}
+
+/* ---- transmit side on the device ----------------------- */
+
+extern "C" int wb_tx_synthesize(wb_engine *e, const uint8_t *payloads, const wb_tx_config *cfg, uint64_t *nsamp_per_stream)
+{
+    if (!e || !payloads || !cfg) return wb_fail(WB_EINVAL, "null argument");
+    if (cfg->struct_size != sizeof(wb_tx_config)) return wb_fail(WB_EINVAL, "wb_tx_config.struct_size mismatch");
+    if (cfg->n_packets <= 0 || cfg->lead_in_bits < 0 || cfg->gap_bits < 0 || cfg->tail_bits < 0) return wb_fail(WB_EINVAL, "bad wb_tx_config");
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    if (e->resident_mode) return wb_fail(WB_EINVAL, "engine is in resident (wb_dev_set_fill) mode");
+    CU(cudaSetDevice(e->cfg.device));
+    const int n = e->cfg.n_streams, M = e->fp.M, Ts = e->fp.Ts, Nsym = e->fp.Nsym, framing = e->cfg.framing;
+    const int bps = (M == 2) ? 1 : 2;
+    const int frame_bits = framing == WB_FRAMING_V1 ? WB_TX_RAW_BYTES * 10 : (framing == WB_FRAMING_V2 ? WB_TX_RAW_BYTES * 8 : WB_PACKET_BYTES * 8);
+    unsigned long long nbits = (unsigned long long)cfg->lead_in_bits + (unsigned long long)cfg->n_packets * (frame_bits + cfg->gap_bits) + cfg->tail_bits;
+    const unsigned long long per_call = (unsigned long long)Nsym * bps;
+    const unsigned long long n_calls = (nbits + per_call - 1) / per_call;
+    nbits = n_calls * per_call;
+    const unsigned long long nsamp = n_calls * Nsym * Ts;
+    for (int s = 0; s < n; s++)
+        if (WB_HEADROOM + e->fill[s] + nsamp > e->in_cap) return wb_fail(WB_ERANGE, "stream %d: chunk capacity exceeded (%llu samples)", s, nsamp);
+
+    const bool noise = !std::isnan(cfg->ebno_db);
+    const bool cf32 = e->fp.in_fmt == WB_FMT_CF32;
+    uint8_t *d_pl = nullptr;
+    float *d_work = nullptr, *d_peak = nullptr;
+    unsigned long long *d_off = nullptr;
+    auto cleanup = [&]() { cudaFree(d_pl); cudaFree(d_work); cudaFree(d_peak); cudaFree(d_off); };
+#define CT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
+        return wb_fail(e_ == cudaErrorMemoryAllocation ? WB_ENOMEM : WB_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
+    const size_t pl_bytes = (size_t)n * cfg->n_packets * WB_PACKET_BYTES;
+    CT(cudaMalloc(&d_pl, pl_bytes));
+    CT(cudaMemcpyAsync(d_pl, payloads, pl_bytes, cudaMemcpyHostToDevice, e->stream));
+    /* the bit rows stay with the engine until the next synthesis (test tap) */
+    cudaFree(e->d_tx_bits); e->d_tx_bits = nullptr;
+    e->tx_bits_stride = (nbits + 63) & ~63ULL; e->tx_nbits = nbits;
+    CT(cudaMalloc(&e->d_tx_bits, e->tx_bits_stride * n));
+    CT(cudaMemsetAsync(e->d_tx_bits, 1, e->tx_bits_stride * n, e->stream));          /* idle = '1' */
+    if (!e->d_hrows) {
+        CT(cudaMalloc(&e->d_hrows, sizeof(wb_hrows)));
+        CT(cudaMemcpyAsync(e->d_hrows, wb_hrows, sizeof(wb_hrows), cudaMemcpyHostToDevice, e->stream));
+    }
+    std::vector<unsigned long long> off(n);
+    for (int s = 0; s < n; s++) off[s] = WB_HEADROOM + (e->fill[s] - e->cursor[s].in_fill);
+    CT(cudaMalloc(&d_off, sizeof(unsigned long long) * n));
+    CT(cudaMemcpyAsync(d_off, off.data(), sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, e->stream));
+    CT(cudaMalloc(&d_peak, sizeof(float) * n));
+    CT(cudaMemsetAsync(d_peak, 0, sizeof(float) * n, e->stream));
+    if (!cf32) CT(cudaMalloc(&d_work, sizeof(float2) * nsamp * n));
+
+    wb_tx_args ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.payloads = d_pl; ta.bits = e->d_tx_bits; ta.bits_stride = e->tx_bits_stride; ta.n_streams = n; ta.n_packets = cfg->n_packets;
+    ta.framing = framing; ta.lead_in = cfg->lead_in_bits; ta.gap = cfg->gap_bits; ta.frame_bits = frame_bits;
+    ta.hrows = e->d_hrows; ta.scramble = e->d_scramble;
+    const long long npk = (long long)n * cfg->n_packets;
+    if (framing == WB_FRAMING_NONE) {
+        wb_tx_raw_bits_kernel<<<(unsigned)((npk * WB_PACKET_BYTES * 8 + 255) / 256), 256, 0, e->stream>>>(ta);
+    } else {
+        wb_tx_frame_kernel<<<(unsigned)((npk + 3) / 4), 128, 0, e->stream>>>(ta);
+    }
+    wb_mod_args ma;
+    memset(&ma, 0, sizeof(ma));
+    ma.bits = e->d_tx_bits; ma.bits_stride = e->tx_bits_stride; ma.peak = d_peak; ma.n_streams = n; ma.M = M; ma.Ts = Ts; ma.Nsym = Nsym;
+    ma.n_calls = n_calls; ma.seed = cfg->seed; ma.unit = noise ? 1 : 0;
+    if (cf32) { ma.work = reinterpret_cast<float *>(e->d_in); ma.work_stride = e->in_stride / sizeof(float2); ma.work_off = d_off; }
+    else { ma.work = d_work; ma.work_stride = nsamp; ma.work_off = nullptr; }
+    for (int m = 0; m < M; m++) {                  /* dosc_f[m], src/fsk.c:1174-1176 */
+        hcpx d = hcexpj((float)(2 * M_PI * ((float)(cfg->f1_tx + (cfg->fs_tx * m)) / (float)(e->fp.Fs))));
+        ma.dosc[m] = make_float2(d.r, d.i);
+    }
+    if (noise) {                                   /* generate_lowsnr.py:70-77 with unit signal variance */
+        const double ebno = pow(10.0, (double)cfg->ebno_db / 10.0);
+        const double nvar = (double)e->fp.Fs / ((double)e->fp.Rs * ebno * bps);
+        ma.sigma = (float)sqrt(nvar / 2.0);
+    }
+    wb_tx_mod_kernel<<<(n + 31) / 32, 32, 0, e->stream>>>(ma);
+    if (noise || !cf32) {
+        dim3 grid(std::max(1u, std::min(64u, (unsigned)((nsamp + 255) / 256))), (unsigned)n);
+        wb_tx_scale_kernel<<<grid, 256, 0, e->stream>>>(ma.work, ma.work_stride, ma.work_off, d_peak, noise ? 1 : 0, e->d_in, e->in_stride,
+                                                        d_off, e->fp.in_fmt, nsamp, n);
+    }
+    e->launches += 3;
+    CT(cudaStreamSynchronize(e->stream));
+    CT(cudaGetLastError());
+#undef CT
+    cleanup();
+    for (int s = 0; s < n; s++) e->fill[s] += nsamp;
+    for (int s = 1; s < n && e->uniform_fill; s++)
+        if (e->fill[s] - e->cursor[s].in_fill != e->fill[0] - e->cursor[0].in_fill) e->uniform_fill = false;
+    if (nsamp_per_stream) *nsamp_per_stream = nsamp;
+    return WB_OK;
+}
+
+extern "C" int wb_dev_read_input(wb_engine *e, int stream, uint64_t first, uint64_t nsamp, void *out)
+{
+    if (!e || !out) return wb_fail(WB_EINVAL, "null argument");
+    if (stream < 0 || stream >= e->cfg.n_streams) return wb_fail(WB_EINVAL, "stream %d out of range", stream);
+    if (WB_HEADROOM + first + nsamp > e->in_cap) return wb_fail(WB_ERANGE, "beyond the input row");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpy(out, e->d_in + (size_t)stream * e->in_stride + (WB_HEADROOM + first) * e->fp.in_bps, nsamp * e->fp.in_bps,
+                  cudaMemcpyDeviceToHost));
+    return WB_OK;
+}
+
+extern "C" int wb_tx_read_bits(wb_engine *e, int stream, uint8_t *bits, size_t cap, size_t *nout)
+{
+    if (!e || !bits || !nout) return wb_fail(WB_EINVAL, "null argument");
+    if (stream < 0 || stream >= e->cfg.n_streams) return wb_fail(WB_EINVAL, "stream %d out of range", stream);
+    if (!e->d_tx_bits) return wb_fail(WB_EINVAL, "no wb_tx_synthesize yet");
+    if (cap < e->tx_nbits) return wb_fail(WB_ERANGE, "need room for %llu bits", e->tx_nbits);
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaMemcpy(bits, e->d_tx_bits + (size_t)stream * e->tx_bits_stride, e->tx_nbits, cudaMemcpyDeviceToHost));
+    *nout = (size_t)e->tx_nbits;
     return WB_OK;
 }
 

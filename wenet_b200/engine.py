@@ -58,6 +58,12 @@ assert CODEWORD_DTYPE.itemsize == 280
 
 # every symbol include/wenet_b200.h declares: (name, restype, argtypes)
 _VP, _SZ, _U64 = C.c_void_p, C.c_size_t, C.c_uint64
+class WbTxConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("n_packets", C.c_int32), ("lead_in_bits", C.c_int32), ("gap_bits", C.c_int32),
+                ("tail_bits", C.c_int32), ("f1_tx", C.c_int32), ("fs_tx", C.c_int32), ("ebno_db", C.c_float),
+                ("seed", C.c_uint64)]
+
+
 ABI = [
     ("wb_create", C.c_int, [C.POINTER(WbConfig), C.POINTER(_VP)]),
     ("wb_destroy", None, [_VP]),
@@ -77,6 +83,9 @@ ABI = [
     ("wb_clear_estimators", C.c_int, [_VP]),
     ("wb_ldpc_decode_batch", C.c_int, [_VP, _VP, _SZ, C.c_int, _VP, _VP, _VP]),
     ("wb_sd_to_llr_batch", C.c_int, [_VP, _VP, _SZ, _VP]),
+    ("wb_tx_synthesize", C.c_int, [_VP, _VP, C.POINTER(WbTxConfig), C.POINTER(_U64)]),
+    ("wb_tx_read_bits", C.c_int, [_VP, C.c_int, _VP, _SZ, C.POINTER(_SZ)]),
+    ("wb_dev_read_input", C.c_int, [_VP, C.c_int, _U64, _U64, _VP]),
     ("wb_dev_input", C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_U64), C.POINTER(_U64)]),
     ("wb_dev_set_fill", C.c_int, [_VP, _U64]),
     ("wb_dev_replicate", C.c_int, [_VP, C.c_int, _U64, _U64]),
@@ -322,6 +331,32 @@ class Engine:
         p, stride, cap = _VP(), C.c_uint64(0), C.c_uint64(0)
         self._check(self.lib.wb_dev_input(self.h, C.byref(p), C.byref(stride), C.byref(cap)))
         return p.value, stride.value, cap.value
+
+    # ---- transmit side on the device ----
+    def tx_synthesize(self, payloads, f1_tx, fs_tx, ebno_db=None, lead_in=2000, gap=0, tail=400, seed=0):
+        """Build every stream's input on the device, as a wb_feed would have delivered it: payloads[n_streams][n_packets]
+        [256] -> framed (the engine's framing), modulated by the reference's fsk_mod_c arithmetic, optionally AWGN +
+        peak normalisation (benchmarking/generate_lowsnr.py).  Returns the samples appended to every stream."""
+        pl = np.ascontiguousarray(payloads, dtype=np.uint8)
+        if pl.ndim != 3 or pl.shape[0] != self.n_streams or pl.shape[2] != 256:
+            raise ValueError("payloads must be [n_streams][n_packets][256] bytes")
+        cfg = WbTxConfig(C.sizeof(WbTxConfig), pl.shape[1], lead_in, gap, tail, int(f1_tx), int(fs_tx),
+                         float("nan") if ebno_db is None else float(ebno_db), int(seed))
+        ns = _U64(0)
+        self._check(self.lib.wb_tx_synthesize(self.h, _ptr(pl), C.byref(cfg), C.byref(ns)))
+        return int(ns.value)
+
+    def tx_read_bits(self, stream, cap=1 << 24):
+        bits = np.zeros(cap, dtype=np.uint8)
+        n = _SZ(0)
+        self._check(self.lib.wb_tx_read_bits(self.h, stream, _ptr(bits), cap, C.byref(n)))
+        return bits[:n.value].copy()
+
+    def dev_read_input(self, stream, nsamp, first=0):
+        """samples [first, first + nsamp) of a stream's resident input row, in the engine's input format (test tap)"""
+        out = np.zeros(nsamp * FMT_ELEMS[self.fmt], dtype=FMT_DTYPE[self.fmt])
+        self._check(self.lib.wb_dev_read_input(self.h, stream, first, nsamp, _ptr(out)))
+        return out
 
     def dev_set_fill(self, nsamp):
         self._check(self.lib.wb_dev_set_fill(self.h, nsamp))
