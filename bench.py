@@ -241,7 +241,8 @@ def workload_config(args, world):
             "streams_per_gpu": args.streams, "chunk_samples": args.chunk, "in_fmt": "cf32", "framing": "v1",
             "ldpc_max_iter": 10, "parallelism": "stream-sharded x%d, no collective" % world,
             "l2": "inputs (%.1f GB per step per GPU) larger than L2" % (args.streams * args.chunk * 8 / 1e9),
-            "e2e_in_fmt": "cs16 (the reference arm's input bytes)", "e2e_host_bytes_per_step": args.e2e_bytes}
+            "e2e_in_fmt": "cs16 (the reference arm's input bytes)", "e2e_host_bytes_per_step": args.e2e_bytes,
+            "synth": args.synth}
 
 
 def main():
@@ -258,6 +259,9 @@ def main():
     ap.add_argument("--mode", default="v1", choices=["v1", "v2", "fsk4"],
                     help="v1 = the headline workload; v2 (960000/96000, wenet_ldpc framing) and fsk4 (4-FSK demod only, "
                          "BASELINE configs[4]) are exploration modes: no e2e / cpu_baseline, not the graded line")
+    ap.add_argument("--synth", default="host", choices=["host", "device"],
+                    help="host = 40 seeded numpy streams (with transmitter clock offsets) replicated on the device (default); "
+                         "device = every stream distinct, built in HBM by wb_tx_synthesize (frame_packet + fsk_mod_c + AWGN)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -307,13 +311,26 @@ def main():
     ekw = {"v1": dict(framing="v1"), "v2": dict(Fs=960000, Rs=96000, framing="v2"), "fsk4": dict(M=4, framing="none")}[args.mode]
 
     eng = E.Engine(n, in_fmt="cf32", chunk_samples=chunk, device=local, **ekw)
-    eng.feed(sources + [None] * (n - n_src))
-    eng.sync()
-    eng.dev_replicate(n_src, chunk, 4096 + 16 * 37)     # stream s = source s % n_src rotated by (s // n_src) * 4688 samples
-    eng.dev_set_fill(chunk)
+    fill = chunk
+    if args.synth == "device" and args.mode != "fsk4":
+        from wenet_b200 import siggen
+        cfgs = siggen.V2 if args.mode == "v2" else siggen.V1
+        ts = cfgs["Fs"] // cfgs["Rs"]
+        frame_samples = (343 * (10 if args.mode == "v1" else 8)) * ts
+        npk = max(1, (chunk - 2448 * ts) // frame_samples)
+        rng = np.random.default_rng(4242 + rank)
+        pl = rng.integers(0, 256, size=(n, npk, 256), dtype=np.uint8)
+        pl[:, :, 0] = 0x55
+        ebno = np.array([EBNO_SWEEP[s_ % len(EBNO_SWEEP)] for s_ in range(n)], dtype=np.float32)
+        fill = eng.tx_synthesize(pl, int(cfgs["f_lo"]), int(cfgs["f_hi"] - cfgs["f_lo"]), ebno_db=ebno, seed=rank)
+    else:
+        eng.feed(sources + [None] * (n - n_src))
+        eng.sync()
+        eng.dev_replicate(n_src, chunk, 4096 + 16 * 37)     # stream s = source s % n_src rotated by (s // n_src) * 4688 samples
+    eng.dev_set_fill(fill)
 
     def one_step():
-        eng.dev_set_fill(chunk)
+        eng.dev_set_fill(fill)
         eng.process()
 
     attempts = 0

@@ -160,6 +160,8 @@ typedef struct wb_tx_config {
     int32_t  f1_tx, fs_tx;     /* Hz: tone of symbol 0 and tone spacing (tx_f1 / tx_fs of fsk_create_hbr, src/fsk.h:110) */
     float    ebno_db;          /* AWGN at this Eb/N0; NaN = none (the reference modulator's output as it is) */
     uint64_t seed;             /* noise generator seed */
+    const float *ebno_db_per_stream;   /* host, [n_streams]: overrides ebno_db stream by stream (NaN entries = no noise
+                                          is not supported here: all streams are noisy or none); NULL = ebno_db for all */
 } wb_tx_config;
 /* payloads: host memory, [n_streams][n_packets][256] bytes */
 int  wb_tx_synthesize(wb_engine *e, const uint8_t *payloads, const wb_tx_config *cfg, uint64_t *nsamp_per_stream);

@@ -1245,12 +1245,12 @@ extern "C" int wb_tx_synthesize(wb_engine *e, const uint8_t *payloads, const wb_
     for (int s = 0; s < n; s++)
         if (WB_HEADROOM + e->fill[s] + nsamp > e->in_cap) return wb_fail(WB_ERANGE, "stream %d: chunk capacity exceeded (%llu samples)", s, nsamp);
 
-    const bool noise = !std::isnan(cfg->ebno_db);
+    const bool noise = cfg->ebno_db_per_stream != nullptr || !std::isnan(cfg->ebno_db);
     const bool cf32 = e->fp.in_fmt == WB_FMT_CF32;
     uint8_t *d_pl = nullptr;
-    float *d_work = nullptr, *d_peak = nullptr;
+    float *d_work = nullptr, *d_peak = nullptr, *d_sigma = nullptr;
     unsigned long long *d_off = nullptr;
-    auto cleanup = [&]() { cudaFree(d_pl); cudaFree(d_work); cudaFree(d_peak); cudaFree(d_off); };
+    auto cleanup = [&]() { cudaFree(d_pl); cudaFree(d_work); cudaFree(d_peak); cudaFree(d_off); cudaFree(d_sigma); };
 #define CT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
         return wb_fail(e_ == cudaErrorMemoryAllocation ? WB_ENOMEM : WB_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
     const size_t pl_bytes = (size_t)n * cfg->n_packets * WB_PACKET_BYTES;
@@ -1294,10 +1294,21 @@ extern "C" int wb_tx_synthesize(wb_engine *e, const uint8_t *payloads, const wb_
         hcpx d = hcexpj((float)(2 * M_PI * ((float)(cfg->f1_tx + (cfg->fs_tx * m)) / (float)(e->fp.Fs))));
         ma.dosc[m] = make_float2(d.r, d.i);
     }
+    std::vector<float> sig;
     if (noise) {                                   /* generate_lowsnr.py:70-77 with unit signal variance */
-        const double ebno = pow(10.0, (double)cfg->ebno_db / 10.0);
-        const double nvar = (double)e->fp.Fs / ((double)e->fp.Rs * ebno * bps);
-        ma.sigma = (float)sqrt(nvar / 2.0);
+        auto sigma_of = [&](double db) { return (float)sqrt((double)e->fp.Fs / ((double)e->fp.Rs * pow(10.0, db / 10.0) * bps) / 2.0); };
+        if (cfg->ebno_db_per_stream) {
+            sig.resize(n);
+            for (int s = 0; s < n; s++) {
+                if (std::isnan(cfg->ebno_db_per_stream[s])) { cleanup(); return wb_fail(WB_EINVAL, "ebno_db_per_stream[%d] is NaN", s); }
+                sig[s] = sigma_of(cfg->ebno_db_per_stream[s]);
+            }
+            CT(cudaMalloc(&d_sigma, sizeof(float) * n));
+            CT(cudaMemcpyAsync(d_sigma, sig.data(), sizeof(float) * n, cudaMemcpyHostToDevice, e->stream));
+            ma.sigma_per_stream = d_sigma;
+        } else {
+            ma.sigma = sigma_of(cfg->ebno_db);
+        }
     }
     wb_tx_mod_kernel<<<(n + 31) / 32, 32, 0, e->stream>>>(ma);
     if (noise || !cf32) {

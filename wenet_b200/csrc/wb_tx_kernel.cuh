@@ -159,6 +159,7 @@ struct wb_mod_args {
     unsigned long long n_calls;  /* fsk_mod_c calls per stream */
     float2 dosc[WB_MAXM];        /* comp_exp_j(2 pi (f1 + m fs)/Fs), host glibc */
     float sigma;                 /* per-component noise std on the unit-amplitude signal; 0 = none */
+    const float *sigma_per_stream;   /* [n_streams] or NULL */
     int unit;                    /* 1: halve the modulator output (unit amplitude) before noise */
     unsigned long long seed;
 };
@@ -174,6 +175,7 @@ wb_tx_mod_kernel(wb_mod_args a)
     float2 ph = make_float2(1.0f, 0.0f);                          /* comp_exp_j(0), src/fsk.c:237 */
     const int bps = (a.M == 2) ? 1 : 2;
     float pk = 0.0f;
+    const float sigma = a.sigma_per_stream ? a.sigma_per_stream[s] : a.sigma;
     unsigned long long n = 0, bit_i = 0;
     for (unsigned long long c = 0; c < a.n_calls; c++) {
         for (int i = 0; i < a.Nsym; i++) {
@@ -187,12 +189,12 @@ wb_tx_mod_kernel(wb_mod_args a)
                 t.y = __fadd_rn(__fmul_rn(ph.x, dph.y), __fmul_rn(ph.y, dph.x));
                 ph = t;
                 float2 y = a.unit ? ph : make_float2(__fmul_rn(2.0f, ph.x), __fmul_rn(2.0f, ph.y));
-                if (a.sigma > 0.0f) {
+                if (sigma > 0.0f) {
                     const uint4 r = wb_philox(make_uint4((unsigned)n, (unsigned)(n >> 32), (unsigned)s, 0x57454e45u),
                                               make_uint2((unsigned)a.seed, (unsigned)(a.seed >> 32)));
                     const float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
                     const float u2 = ((float)(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
-                    const float rad = a.sigma * sqrtf(-2.0f * logf(u1));
+                    const float rad = sigma * sqrtf(-2.0f * logf(u1));
                     float sn, cs;
                     sincosf(6.28318530717958647692f * u2, &sn, &cs);
                     y.x += rad * cs; y.y += rad * sn;

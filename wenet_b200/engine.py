@@ -61,7 +61,7 @@ _VP, _SZ, _U64 = C.c_void_p, C.c_size_t, C.c_uint64
 class WbTxConfig(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("n_packets", C.c_int32), ("lead_in_bits", C.c_int32), ("gap_bits", C.c_int32),
                 ("tail_bits", C.c_int32), ("f1_tx", C.c_int32), ("fs_tx", C.c_int32), ("ebno_db", C.c_float),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("ebno_db_per_stream", C.c_void_p)]
 
 
 ABI = [
@@ -340,8 +340,14 @@ class Engine:
         pl = np.ascontiguousarray(payloads, dtype=np.uint8)
         if pl.ndim != 3 or pl.shape[0] != self.n_streams or pl.shape[2] != 256:
             raise ValueError("payloads must be [n_streams][n_packets][256] bytes")
+        per = None
+        if ebno_db is not None and np.ndim(ebno_db) == 1:       # one Eb/N0 per stream
+            per = np.ascontiguousarray(ebno_db, dtype=np.float32)
+            if per.size != self.n_streams:
+                raise ValueError("ebno_db: one value or one per stream")
         cfg = WbTxConfig(C.sizeof(WbTxConfig), pl.shape[1], lead_in, gap, tail, int(f1_tx), int(fs_tx),
-                         float("nan") if ebno_db is None else float(ebno_db), int(seed))
+                         float("nan") if (ebno_db is None or per is not None) else float(ebno_db), int(seed),
+                         per.ctypes.data if per is not None else None)
         ns = _U64(0)
         self._check(self.lib.wb_tx_synthesize(self.h, _ptr(pl), C.byref(cfg), C.byref(ns)))
         return int(ns.value)
