@@ -28,3 +28,11 @@ llr = np.random.default_rng(0).standard_normal((4, 2580)).astype(np.float32) * 3
 e = E.Engine(1, framing="v1", chunk_samples=4096)
 print("ldpc iters", e.ldpc_decode_batch(llr, 10)[1])
 e.close()
+# transmit side on the device, then the engine decodes its own signal
+pl = np.random.default_rng(1).integers(0, 256, size=(3, 2, 256), dtype=np.uint8)
+for fmt, fr, cfg in (("cf32", "v1", siggen.V1), ("cs16", "v2", siggen.V2)):
+    e = E.Engine(3, Fs=cfg["Fs"], Rs=cfg["Rs"], in_fmt=fmt, framing=fr, chunk_samples=1 << 17)
+    e.tx_synthesize(pl, int(cfg["f_lo"]), int(cfg["f_hi"] - cfg["f_lo"]), ebno_db=10.0, seed=3)
+    e.process(); e.sync()
+    print("tx", fmt, fr, "packets", [len(e.drain_packets(s)) // 256 for s in range(3)])
+    e.close()
