@@ -57,10 +57,20 @@ def test_x87_emulation(hm):
 def test_phi0_tables(hm, oracle_port):
     rng = np.random.default_rng(2)
     x = np.concatenate([rng.uniform(-1, 40, 500000), 2.0 ** rng.uniform(-20, 17, 500000),
-                        [0.0, -0.0, np.nan, np.inf, -np.inf, 32768, 32767.99, 1e9, 10, 9.9999]]).astype(np.float32)
+                        [0.0, -0.0, np.nan, -np.nan, np.inf, -np.inf, 32768, 32767.99, 1e9, 10, 9.9999, 16, 15.999999]]).astype(np.float32)
+    # every breakpoint of the step function and its float neighbours
+    brk = np.float32(2.0) ** np.arange(-15, 5, dtype=np.float32)
+    grid = np.concatenate([brk, brk * np.float32(2 ** -0.5), np.arange(1, 10.5, 1 / 16, dtype=np.float32)])
+    near = np.concatenate([np.nextafter(grid, np.float32(0)), grid, np.nextafter(grid, np.float32(100))])
+    q = (np.arange(0, 70000, dtype=np.float64) / 65536.0).astype(np.float32)          # every Q16 integer below 1.07
+    x = np.concatenate([x, near, q, np.nextafter(q, np.float32(0)), np.nextafter(q, np.float32(100))]).astype(np.float32)
     ref = oracle_port.phi0(x)
-    for name in ("wbh_phi0", "wbh_phi0_compact", "wbh_phi0_pairs"):
-        got = _call(getattr(hm, name), x, out_dtype=np.float32)
+    for name in ("wbh_phi0", "wbh_phi0_pairs", "wbh_phi0_flag"):
+        fn = getattr(hm, name)
+        fn.restype = C.c_long
+        got = np.full(x.size, -1.0, dtype=np.float32)
+        rc = fn(x.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p), C.c_long(x.size))
+        assert name == "wbh_phi0" or rc == 0, (name, rc)      # the table builders report a layout they cannot express
         assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), name
     assert math.isclose(float(oracle_port.phi0(np.float32([0.5]))[0]), 1.5735153, rel_tol=1e-7)
 

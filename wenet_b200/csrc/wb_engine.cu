@@ -80,7 +80,7 @@ struct wb_engine {
     uint16_t *d_crc_tab;
     unsigned crc0;
     uint8_t *d_scramble;
-    wb_phi0_pairs *d_lut;
+    wb_phi0_flag *d_lut;
     /* resident LDPC benchmark */
     float *d_bench_llr;
     uint8_t *d_bench_bits;
@@ -244,17 +244,9 @@ static int upload_tables(wb_engine *e)
     for (int l = 0; l < nl; l++) if (fac[2 * l] != 4 && fac[2 * l] != 2) return wb_fail(WB_EINVAL, "unsupported FFT radix");
     for (int l = 0; l < nl - 1; l++) if (fac[2 * l] != 4) return wb_fail(WB_EINVAL, "unsupported FFT factorisation");
     fft_perm(perm, 0, 0, 1, fac);
-    fp.n_levels = nl;
-    {
-        int fstride = 1;
-        for (int l = 0; l < nl; l++) {             /* top level first in fac[], leaf first in lev_* */
-            int dst = nl - 1 - l;
-            fp.lev_p[dst] = fac[2 * l]; fp.lev_m[dst] = fac[2 * l + 1]; fp.lev_fstride[dst] = fstride;
-            int sh = 0; while ((1 << sh) < fac[2 * l + 1]) sh++;
-            fp.lev_sh[dst] = sh;
-            fstride *= fac[2 * l];
-        }
-    }
+    /* the kernel's FFT schedule is compiled in: 256 = 4 x 4 x 4 x 4, leaf first (kiss_fft factors 4s first) */
+    if (nl != 4) return wb_fail(WB_EINVAL, "FFT schedule of %d levels: the kernels are built for 4 x 4 x 4 x 4", nl);
+    for (int l = 0; l < nl; l++) if (fac[2 * l] != 4) return wb_fail(WB_EINVAL, "FFT radix %d at level %d: the kernels are built for radix 4", fac[2 * l], l);
     /* fine-timing oscillator, reference src/fsk.c:858-873 */
     {
         hcpx d = hcexpj((float)(2 * M_PI * ((float)fp.Rs / (float)(fp.P * fp.Rs))));
@@ -280,7 +272,7 @@ static int upload_tables(wb_engine *e)
     CU(cudaMemcpy(e->d_tables, h.data(), off, cudaMemcpyHostToDevice));
     unsigned char *base = (unsigned char *)e->d_tables;
     fp.hann = (const float *)(base + o_hann); fp.tw = (const float2 *)(base + o_tw);
-    fp.perm = (const uint16_t *)(base + o_perm); fp.pft = (const float2 *)(base + o_pft);
+    fp.perm = (const uint16_t *)(base + o_perm);
     fp.dphi = (const float2 *)(base + o_dphi); fp.back = (const float2 *)(base + o_back);
 
     /* LDPC edge table: message word of (data column i, k-th check in H_cols order) */
@@ -313,8 +305,8 @@ static int upload_tables(wb_engine *e)
     CU(cudaMemcpy(e->d_crc_tab, crc_tab.data(), sizeof(uint16_t) * 2048, cudaMemcpyHostToDevice));
     CU(cudaMalloc(&e->d_scramble, WB_SCRAMBLE_LEN));
     CU(cudaMemcpy(e->d_scramble, wb_scramble_neg, WB_SCRAMBLE_LEN, cudaMemcpyHostToDevice));
-    static wb_phi0_pairs lut;
-    if (wb_phi0_build_pairs(&lut) != 0) return wb_fail(WB_EINVAL, "phi0 table: two breakpoints in one bucket");
+    static wb_phi0_flag lut;
+    if (wb_phi0_build_flag(&lut) != 0) return wb_fail(WB_EINVAL, "phi0 table: the step function does not fit the flag form");
     CU(cudaMalloc(&e->d_lut, sizeof(lut)));
     CU(cudaMemcpy(e->d_lut, &lut, sizeof(lut), cudaMemcpyHostToDevice));
     return WB_OK;

@@ -47,14 +47,6 @@ void wbh_phi0(const float *x, float *out, long n)
     for (i = 0; i < n; i++) out[i] = wb_phi0_eval(&lut, x[i]);
 }
 
-void wbh_phi0_compact(const float *x, float *out, long n)
-{
-    long i;
-    static wb_phi0_compact c;
-    wb_phi0_build_compact(&c);
-    for (i = 0; i < n; i++) out[i] = wb_phi0_eval_compact(&c, x[i]);
-}
-
 long wbh_phi0_pairs(const float *x, float *out, long n)
 {
     long i;
@@ -62,6 +54,16 @@ long wbh_phi0_pairs(const float *x, float *out, long n)
     int rc = wb_phi0_build_pairs(&t);
     if (rc) return rc;
     for (i = 0; i < n; i++) out[i] = wb_phi0_eval_pairs(&t, x[i]);
+    return 0;
+}
+
+long wbh_phi0_flag(const float *x, float *out, long n)
+{
+    long i;
+    static wb_phi0_flag t;
+    int rc = wb_phi0_build_flag(&t);
+    if (rc) return rc;
+    for (i = 0; i < n; i++) out[i] = wb_phi0_eval_flag(&t, x[i]);
     return 0;
 }
 

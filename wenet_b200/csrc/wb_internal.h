@@ -70,8 +70,6 @@ struct wb_fsk_params {
     int nmax;                 /* N + Ts/2: longest frame */
     int f_min, f_max, f_zero; /* estimator bin limits, reference src/fsk.c:568-570 */
     float tc;                 /* 0.95 * Ndft / Fs, reference src/fsk.c:573 */
-    int n_levels;             /* FFT schedule, leaf first */
-    int lev_p[WB_MAX_LEVELS], lev_m[WB_MAX_LEVELS], lev_fstride[WB_MAX_LEVELS], lev_sh[WB_MAX_LEVELS];
     int in_fmt, in_bps;       /* bytes per input sample */
     int stats;                /* WB_FLAG_STATS: per-frame Eb/N0 terms and eye-diagram tap */
     int b1_w;                 /* warps sharing the sequential mixer phase, and their frame segments */
@@ -82,7 +80,6 @@ struct wb_fsk_params {
     const float  *hann;       /* [Ndft]       reference src/fsk.c:94-111 */
     const float2 *tw;         /* [Ndft]       kiss_fft twiddles, reference src/kiss_fft.c:357-363 */
     const uint16_t *perm;     /* [Ndft]       leaf load order of the DIT recursion */
-    const float2 *pft;        /* [nint]       fine-timing oscillator, reference src/fsk.c:858-873 */
     int pft_steady;           /* P == Ts and pft[i] == pft[i - P] for every i >= (WB_PFT_NT + 1) * P: see wb_b3_chain */
     const float2 *dphi;       /* [Ndft/2]     comp_exp_j(2 pi f/Fs), f = bin*Fs/Ndft, src/fsk.c:763 */
     const float2 *back;       /* [3][Ndft/2]  phase back-off for nin = N-Ts/2, N, N+Ts/2, src/fsk.c:758 */

@@ -50,7 +50,7 @@ struct wb_ldpc_args {
     const uint16_t *crc_tab;    /* [2048] CRC contribution of payload bit i */
     unsigned crc0;              /* CRC of 256 zero bytes */
     const uint8_t *scramble;    /* [1000] 1 = negate */
-    const wb_phi0_pairs *lut;
+    const wb_phi0_flag *lut;
 };
 
 /* symbol index inside a collected packet of codeword element c */
@@ -129,19 +129,24 @@ wb_llr_scale_kernel(const float *sd, const double *c4, float *llr, long long n_b
 
 struct wb_ldpc_smem {
     float msg[WB_LDPC_NMSG];            /* 28 896 B */
-    wb_phi0_pairs lut;                  /*  9 232 B */
+    wb_phi0_flag lut;                   /*  5 224 B */
     unsigned ballot[(WB_NCODE + 31) / 32 + 1];   /* hard decisions, bit l of word w = variable 32w + l */
     unsigned crc_part[4];
 };
 
-/* phi0 (reference src/phi0.c:13-218): two independent 8-byte loads and one compare, see wb_phi0.h */
-__device__ __forceinline__ float wb_phi0_s(const wb_phi0_pairs &lut, float x)
+/* phi0 (reference src/phi0.c:13-218): one 4-byte load; the few buckets with a breakpoint inside carry a flag and
+   take two more loads and the compare (flag form of wb_phi0.h).  The decoder is shared-memory-bandwidth bound and
+   these look-ups were two thirds of its traffic as 16 bytes each. */
+__device__ __forceinline__ float wb_phi0_s(const wb_phi0_flag &lut, float x)
 {
     int b = ((int)__float_as_uint(x) >> 17) - (WB_PHI0_EXP0 << 6);
     b = max(0, min(b, WB_PHI0_NBUCKET));
-    const float2 p0 = *reinterpret_cast<const float2 *>(&lut.pt[b]);
-    const float2 p1 = *reinterpret_cast<const float2 *>(&lut.pt[b + 1]);
-    return (x < p0.x) ? p0.y : p1.y;
+    float v = lut.val[b];
+    if ((int)__float_as_uint(v) < 0) {
+        const int g = b >> 4;
+        v = (x < lut.gthr[g]) ? __uint_as_float(__float_as_uint(v) & 0x7fffffffu) : lut.gvhi[g];
+    }
+    return v;
 }
 
 __device__ __forceinline__ float wb_signed(float mag, unsigned neg)
@@ -172,7 +177,7 @@ wb_ldpc_kernel(wb_ldpc_args a, long long n_direct)
     {
         const unsigned *src = reinterpret_cast<const unsigned *>(a.lut);
         unsigned *dst = reinterpret_cast<unsigned *>(&sm.lut);
-        for (int i = tid; i < (int)(sizeof(wb_phi0_pairs) / 4); i += WB_LDPC_THREADS) dst[i] = src[i];
+        for (int i = tid; i < (int)(sizeof(wb_phi0_flag) / 4); i += WB_LDPC_THREADS) dst[i] = src[i];
     }
     /* LLRs: gather + scale (mode A) or load (mode B); thread tid owns variables tid + 288 r, r = 0..8, for the
        whole decode, so their LLRs stay in registers */

@@ -89,52 +89,6 @@ WB_HD float wb_phi0_eval(const wb_phi0_lut *lut, float x)
 }
 
 
-/* ---- compact form for shared memory (2.8 KB instead of 18 KB) ------------
- * sidx[b] = step the bucket STARTS in; step[s] = {first argument of step s+1, value of step s,
- * value of step s+1}.  A bucket holds at most one breakpoint, so either the bucket's arguments all
- * lie below step[s].thr (-> vlo) or the compare splits them exactly where the reference does. */
-#define WB_PHI0_NSTEP_ENTRIES (WB_PHI0_NSTEPS + 1)
-typedef struct {
-    wb_phi0_entry step[WB_PHI0_NSTEP_ENTRIES];       /* 104 x 16 B */
-    uint8_t sidx[(WB_PHI0_NENTRY + 15) / 16 * 16];   /* 1153 -> 1168 B */
-} wb_phi0_compact;
-
-static inline int wb_phi0_build_compact(wb_phi0_compact *c)
-{
-    int b, k, s;
-    wb_phi0_lut full;
-    if (wb_phi0_build(&full) != 0) return -1;
-    for (s = 0; s < WB_PHI0_NSTEPS; s++) {
-        c->step[s].vlo = wb_phi0_val[s];
-        if (s + 1 < WB_PHI0_NSTEPS) {
-            c->step[s].thr = (float)((double)wb_phi0_brk[s + 1] / 65536.0);
-            c->step[s].vhi = wb_phi0_val[s + 1];
-        } else {
-            c->step[s].thr = 32768.0f;               /* cvttss2si overflow: x >= 32768 -> 10.0 */
-            c->step[s].vhi = 10.0f;
-        }
-        c->step[s].pad = 0.0f;
-    }
-    c->step[WB_PHI0_NSTEPS] = c->step[WB_PHI0_NSTEPS - 1];
-    for (b = 0; b < (int)sizeof(c->sidx); b++) c->sidx[b] = 0;
-    for (b = 0; b < WB_PHI0_NBUCKET; b++) {
-        int E = -14 + b / 64, j = b % 64;
-        int64_t q_first = (((int64_t)(64 + j)) << (E + 30)) >> 20;
-        s = 0;
-        for (k = 0; k < WB_PHI0_NSTEPS; k++) if ((int64_t)wb_phi0_brk[k] <= q_first) s = k;
-        c->sidx[b] = (uint8_t)s;
-    }
-    c->sidx[WB_PHI0_NBUCKET] = (uint8_t)(WB_PHI0_NSTEPS - 1);
-    return 0;
-}
-
-WB_HD float wb_phi0_eval_compact(const wb_phi0_compact *c, float x)
-{
-    wb_phi0_entry en = c->step[c->sidx[wb_phi0_bucket(x)]];
-    return (x < en.thr) ? en.vlo : en.vhi;
-}
-
-
 /* ---- pair form: one level of independent loads ------------------------------
  * pt[b] = {threshold inside bucket b (or +inf), value at the start of bucket b}; a bucket holds at most one
  * breakpoint, after which the value is the one the next bucket starts with:
@@ -166,6 +120,60 @@ WB_HD float wb_phi0_eval_pairs(const wb_phi0_pairs *t, float x)
     const int b = wb_phi0_bucket(x);
     const wb_phi0_pair p0 = t->pt[b], p1 = t->pt[b + 1];
     return (x < p0.thr) ? p0.val : p1.val;
+}
+
+
+/* ---- flag form: one 4-byte load per call -------------------------------------
+ * The decoder is bound by shared-memory bandwidth and the table look-ups are two thirds of its traffic, so the
+ * common case must be one small load.  val[b] = value at the start of bucket b; only a bucket with a breakpoint
+ * strictly inside needs more, and those are few and far apart: from 1 up every step of the reference is a multiple
+ * of 1/16 = a bucket start; below 1 the steps sit one Q16 unit above 2^-j (first bucket of an octave) and at
+ * 2^-j / sqrt 2 (bucket 26 of an octave), so no two of them share a group of 16 buckets (checked when the table is
+ * built).  Such a bucket carries its value with the sign bit set and its group g = b >> 4 holds the threshold and the
+ * value above it:
+ *     v = val[b];  if (v has the sign bit) v = (x < gthr[g]) ? |v| : gvhi[g];
+ * The clamp bucket (x >= 16) is flagged with threshold 32768: 0.0 below, 10.0 from there up and for NaN (the
+ * cvttss2si overflow quirk, the compare is false). */
+#define WB_PHI0_NGROUP (WB_PHI0_NBUCKET / 16 + 1)       /* 72 groups of 16 buckets + the clamp bucket */
+typedef struct {
+    float val[WB_PHI0_NENTRY + 3];                       /* 1153 used */
+    float gthr[WB_PHI0_NGROUP + 3], gvhi[WB_PHI0_NGROUP + 3];
+} wb_phi0_flag;
+
+static inline int wb_phi0_build_flag(wb_phi0_flag *t)
+{
+    wb_phi0_lut full;
+    int b, g, seen[WB_PHI0_NGROUP];
+    if (wb_phi0_build(&full) != 0) return -1;
+    for (g = 0; g < WB_PHI0_NGROUP + 3; g++) { t->gthr[g] = 0.0f; t->gvhi[g] = 0.0f; }
+    for (g = 0; g < WB_PHI0_NGROUP; g++) seen[g] = 0;
+    for (b = 0; b < (int)(sizeof(t->val) / sizeof(float)); b++) t->val[b] = 0.0f;
+    for (b = 0; b < WB_PHI0_NENTRY; b++) {
+        const wb_phi0_entry en = full.e[b];
+        const int inside = (b == WB_PHI0_NBUCKET) || (en.vlo != en.vhi);     /* a compare is needed in this bucket */
+        if (wb_f2u(en.vlo) >> 31) return -2;                                  /* the sign bit is ours */
+        t->val[b] = en.vlo;
+        if (inside) {
+            g = b >> 4;
+            if (seen[g]) return -3;                                           /* two such buckets in one group */
+            seen[g] = 1;
+            t->val[b] = wb_u2f(wb_f2u(en.vlo) | 0x80000000u);
+            t->gthr[g] = en.thr;
+            t->gvhi[g] = en.vhi;
+        }
+    }
+    return 0;
+}
+
+WB_HD float wb_phi0_eval_flag(const wb_phi0_flag *t, float x)
+{
+    const int b = wb_phi0_bucket(x);
+    float v = t->val[b];
+    if (wb_f2u(v) >> 31) {
+        const int g = b >> 4;
+        v = (x < t->gthr[g]) ? wb_u2f(wb_f2u(v) & 0x7fffffffu) : t->gvhi[g];
+    }
+    return v;
 }
 
 #endif /* WB_PHI0_H */
