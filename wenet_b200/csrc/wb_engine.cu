@@ -28,6 +28,7 @@
 #include "wb_deframe_kernel.cuh"
 #include "wb_ldpc_kernel.cuh"
 #include "wb_tx_kernel.cuh"
+#include "wb_vperm.h"
 
 #define WB_HEADROOM 512u    /* samples in front of every input row for the parked remainder (>= WB_MAX_NIN) */
 
@@ -275,9 +276,19 @@ static int upload_tables(wb_engine *e)
     fp.perm = (const uint16_t *)(base + o_perm);
     fp.dphi = (const float2 *)(base + o_dphi); fp.back = (const float2 *)(base + o_back);
 
-    /* LDPC edge table: message word of (data column i, k-th check in H_cols order) */
+    /* LDPC edge table: message words of (data column i, k-th check in H_cols order), k = 0..2, and i itself, listed
+       by variable-pass slot: slot s works on column wb_vperm[s] (an order with few shared-memory bank conflicts,
+       tools/gen_vperm.py; any permutation is correct) */
+    {
+        std::vector<char> seen(WB_NDATA, 0);
+        for (int s = 0; s < WB_NDATA; s++) {
+            if (wb_vperm[s] >= WB_NDATA || seen[wb_vperm[s]]) return wb_fail(WB_EINVAL, "wb_vperm is not a permutation");
+            seen[wb_vperm[s]] = 1;
+        }
+    }
     std::vector<ushort4> vedge(WB_NDATA);
-    for (int i = 0; i < WB_NDATA; i++) {
+    for (int s = 0; s < WB_NDATA; s++) {
+        const int i = wb_vperm[s];
         unsigned short w[3];
         for (int k = 0; k < WB_COLW; k++) {
             int c = wb_hcols[i * WB_COLW + k], found = -1;
@@ -285,7 +296,7 @@ static int upload_tables(wb_engine *e)
             if (found < 0) return wb_fail(WB_EINVAL, "H tables inconsistent");
             w[k] = (unsigned short)(found * WB_NPAR + c);
         }
-        vedge[i] = make_ushort4(w[0], w[1], w[2], 0);
+        vedge[s] = make_ushort4(w[0], w[1], w[2], (unsigned short)i);
     }
     CU(cudaMalloc(&e->d_vedge, sizeof(ushort4) * WB_NDATA));
     CU(cudaMemcpy(e->d_vedge, vedge.data(), sizeof(ushort4) * WB_NDATA, cudaMemcpyHostToDevice));

@@ -17,7 +17,11 @@
  * c_nodes[j].subs[] order (12 H1 columns, parity j-1, parity j) so phi_sum accumulates in the
  * reference's order, and a variable adds its incoming messages in v_nodes[i].subs[] order
  * (H_cols order; checks q, q+1 for parity column q).  516 checks = 2 rounds of 288 threads,
- * 2580 variables = 9 rounds (2592 slots): no tail round.
+ * 2580 variables = 9 rounds (2592 slots): no tail round.  The variable pass gathers from scattered words, so WHICH
+ * data column a thread takes decides the bank conflicts: slot s = thread + 288 * round works on column
+ * vedge[s].w = wb_vperm[s], an order chosen off line for few conflicts (tools/gen_vperm.py: 3.55 -> 1.83 wavefronts
+ * per gather); LLRs are staged through shared memory in natural order and the hard decisions put back in natural
+ * order at the end.
  * HBM traffic per codeword: 3230 (v1) or 2584 (v2) floats in, one 280-byte record out.
  */
 #ifndef WB_LDPC_KERNEL_CUH
@@ -46,7 +50,7 @@ struct wb_ldpc_args {
     int *iters_out, *pcc_out;   /* mode B: [n] */
     int max_iter;
     /* tables */
-    const ushort4 *vedge;       /* [2064] message words of a data column's three edges */
+    const ushort4 *vedge;       /* [2064] by variable-pass slot: message words of the column's three edges, .w = the column */
     const uint16_t *crc_tab;    /* [2048] CRC contribution of payload bit i */
     unsigned crc0;              /* CRC of 256 zero bytes */
     const uint8_t *scramble;    /* [1000] 1 = negate */
@@ -130,7 +134,8 @@ wb_llr_scale_kernel(const float *sd, const double *c4, float *llr, long long n_b
 struct wb_ldpc_smem {
     float msg[WB_LDPC_NMSG];            /* 28 896 B */
     wb_phi0_flag lut;                   /*  5 224 B */
-    unsigned ballot[(WB_NCODE + 31) / 32 + 1];   /* hard decisions, bit l of word w = variable 32w + l */
+    unsigned ballot[(WB_NCODE + 31) / 32 + 1];   /* hard decisions by slot, bit l of word w = slot 32w + l */
+    unsigned nat[(WB_NCODE + 31) / 32 + 1];      /* ... and by variable, after the decode */
     unsigned crc_part[4];
 };
 
@@ -179,15 +184,16 @@ wb_ldpc_kernel(wb_ldpc_args a, long long n_direct)
         unsigned *dst = reinterpret_cast<unsigned *>(&sm.lut);
         for (int i = tid; i < (int)(sizeof(wb_phi0_flag) / 4); i += WB_LDPC_THREADS) dst[i] = src[i];
     }
-    /* LLRs: gather + scale (mode A) or load (mode B); thread tid owns variables tid + 288 r, r = 0..8, for the
-       whole decode, so their LLRs stay in registers */
+    /* LLRs: gather + scale (mode A) or load (mode B), in natural order (coalesced), staged through the message array
+       (not in use yet); then thread tid takes the LLRs of its slots tid + 288 r, r = 0..8, which it owns for the whole
+       decode: registers */
     float llr[9];
     if (direct) {
         const float *src = a.llr_in + slot * WB_NCODE;
 #pragma unroll
         for (int r = 0; r < 9; r++) {
             const int c = tid + r * WB_LDPC_THREADS;
-            llr[r] = (c < WB_NCODE) ? src[c] : 0.0f;
+            if (c < WB_NCODE) sm.msg[c] = src[c];
         }
     } else {
         const float *row = a.sd + (size_t)s * a.sd_stride + a.jobs[slot];
@@ -195,14 +201,21 @@ wb_ldpc_kernel(wb_ldpc_args a, long long n_direct)
 #pragma unroll
         for (int r = 0; r < 9; r++) {
             const int c = tid + r * WB_LDPC_THREADS;
-            llr[r] = 0.0f;
             if (c < WB_NCODE) {
                 float v = row[wb_cw_symbol(a.framing, c)];
                 if (a.framing == WB_FRAMING_V2 && a.scramble[c % WB_SCRAMBLE_LEN]) v = -v;
-                llr[r] = wb_llr_scale(c4, v);
-                if (a.llr_out) a.llr_out[slot * WB_NCODE + c] = llr[r];
+                const float l = wb_llr_scale(c4, v);
+                sm.msg[c] = l;
+                if (a.llr_out) a.llr_out[slot * WB_NCODE + c] = l;
             }
         }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+        const int i = tid + r * WB_LDPC_THREADS;
+        const int v = (i < WB_NDATA) ? (int)a.vedge[i].w : i;         /* parity columns stay in place */
+        llr[r] = (i < WB_NCODE) ? sm.msg[v] : 0.0f;
     }
     __syncthreads();
 
@@ -304,11 +317,24 @@ wb_ldpc_kernel(wb_ldpc_args a, long long n_direct)
         __syncthreads();
     }
 
+    /* ---- hard decisions back into variable order ---- */
+    for (int w = tid; w < (WB_NCODE + 31) / 32 + 1; w += WB_LDPC_THREADS) sm.nat[w] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+        const int i = tid + r * WB_LDPC_THREADS;
+        if (i < WB_NCODE && ((sm.ballot[i >> 5] >> (i & 31)) & 1u)) {
+            const int v = (i < WB_NDATA) ? (int)a.vedge[i].w : i;
+            atomicOr(&sm.nat[v >> 5], 1u << (v & 31));
+        }
+    }
+    __syncthreads();
+
     /* ---- output ---- */
     if (direct) {
         uint8_t *out = a.bits_out + slot * 323;
         for (int B = tid; B < 323; B += WB_LDPC_THREADS)
-            out[B] = (uint8_t)(__brev((sm.ballot[B >> 2] >> (8 * (B & 3))) & 0xffu) >> 24);
+            out[B] = (uint8_t)(__brev((sm.nat[B >> 2] >> (8 * (B & 3))) & 0xffu) >> 24);
         if (tid == 0) { a.iters_out[slot] = result; a.pcc_out[slot] = pcc; }
         return;
     }
@@ -316,7 +342,7 @@ wb_ldpc_kernel(wb_ldpc_args a, long long n_direct)
        (the CRC is affine over GF(2)); same value as reference src/drs232_ldpc.c:91-102 */
     unsigned acc = 0;
     if (tid < 64) {
-        unsigned w = sm.ballot[tid];
+        unsigned w = sm.nat[tid];
         while (w) {
             int l = __ffs(w) - 1;
             w &= w - 1;
@@ -329,10 +355,10 @@ wb_ldpc_kernel(wb_ldpc_args a, long long n_direct)
     __syncthreads();
     wb_codeword *cw = a.cw + slot;
     for (int B = tid; B < 258; B += WB_LDPC_THREADS)
-        cw->bytes[B] = (uint8_t)(__brev((sm.ballot[B >> 2] >> (8 * (B & 3))) & 0xffu) >> 24);
+        cw->bytes[B] = (uint8_t)(__brev((sm.nat[B >> 2] >> (8 * (B & 3))) & 0xffu) >> 24);
     if (tid == 0) {
         unsigned crc = a.crc0 ^ sm.crc_part[0] ^ sm.crc_part[1];
-        unsigned w64 = sm.ballot[64];     /* variables 2048..2079: bytes 256, 257 are its low 16 bits */
+        unsigned w64 = sm.nat[64];     /* variables 2048..2079: bytes 256, 257 are its low 16 bits */
         unsigned b256 = __brev(w64 & 0xffu) >> 24, b257 = __brev((w64 >> 8) & 0xffu) >> 24;
         unsigned tx = b256 + (b257 << 8);
         int ok = (crc == tx);
