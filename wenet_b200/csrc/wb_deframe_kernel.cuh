@@ -9,7 +9,7 @@
  *     not cleared afterwards, so matching resumes over the stream with the packet excised;
  *   - the symbol that completes the UW is not part of the packet.
  *
- * One warp per stream.  While looking, 32 symbols are examined per step: a ballot gives the 32 new
+ * One warp per stream.  While looking, 32 symbols are examined per step (fetched 128 at a time): a ballot gives the 32 new
  * hard bits, lane j forms the window as it stands after symbol j and scores it with one popcount;
  * the first hit (lowest lane) wins.  While collecting, nothing is touched: the packet is recorded
  * as an offset into the row and the scan jumps over it.  Packets are only located here; the symbols
@@ -46,31 +46,45 @@ wb_deframe_kernel(wb_deframe_params p, wb_stream_state *state, wb_cursor *cursor
             ind += n_new; t = n_new;
         }
     }
+    /* 128 symbols are fetched per round (four independent loads per lane in flight: the scan is a chain of
+       L2 round trips otherwise), then examined 32 at a time; a hit restarts the round at the jump target */
     while (t < n_new) {
-        int idx = t + lane;
-        bool valid = idx < n_new;
-        float v = valid ? row[WB_CARRY_CAP + idx] : 0.0f;
-        unsigned nb = __ballot_sync(0xffffffffu, valid && (v < 0.0f));
-        /* window after symbol t+lane: symbols t..t+lane appended, newest in bit 0 */
-        unsigned long long Wj = (W << (lane + 1)) | (unsigned long long)(__brev(nb) >> (31 - lane));
-        int score = __popcll(~(Wj ^ p.uw) & p.uw_mask);
-        unsigned hits = __ballot_sync(0xffffffffu, valid && score >= p.uw_thresh);
-        if (hits) {
-            int first = __ffs(hits) - 1;
-            W = __shfl_sync(0xffffffffu, Wj, first);
-            int start = t + first + 1;               /* first collected symbol */
-            int avail = n_new - start;
-            if (avail >= p.nsym) {
-                if (lane == 0 && nj < job_cap) myjobs[nj] = (unsigned)(WB_CARRY_CAP + start);
-                nj++;
-                t = start + p.nsym;
+        float v4[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int idx = t + 32 * k + lane;
+            v4[k] = (idx < n_new) ? row[WB_CARRY_CAP + idx] : 0.0f;
+        }
+        bool jumped = false;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (jumped || t >= n_new) break;
+            const int idx = t + lane;
+            const bool valid = idx < n_new;
+            const float v = v4[k];
+            unsigned nb = __ballot_sync(0xffffffffu, valid && (v < 0.0f));
+            /* window after symbol t+lane: symbols t..t+lane appended, newest in bit 0 */
+            unsigned long long Wj = (W << (lane + 1)) | (unsigned long long)(__brev(nb) >> (31 - lane));
+            int score = __popcll(~(Wj ^ p.uw) & p.uw_mask);
+            unsigned hits = __ballot_sync(0xffffffffu, valid && score >= p.uw_thresh);
+            if (hits) {
+                int first = __ffs(hits) - 1;
+                W = __shfl_sync(0xffffffffu, Wj, first);
+                int start = t + first + 1;               /* first collected symbol */
+                int avail = n_new - start;
+                if (avail >= p.nsym) {
+                    if (lane == 0 && nj < job_cap) myjobs[nj] = (unsigned)(WB_CARRY_CAP + start);
+                    nj++;
+                    t = start + p.nsym;
+                } else {
+                    collecting = 1; ind = avail; t = n_new;
+                }
+                jumped = true;                           /* the values fetched for this round no longer line up */
             } else {
-                collecting = 1; ind = avail; t = n_new;
+                int nvalid = min(32, n_new - t);
+                W = __shfl_sync(0xffffffffu, Wj, nvalid - 1);
+                t += nvalid;
             }
-        } else {
-            int nvalid = min(32, n_new - t);
-            W = __shfl_sync(0xffffffffu, Wj, nvalid - 1);
-            t += nvalid;
         }
     }
     if (lane == 0) {
