@@ -130,12 +130,14 @@ def ref_binaries():
     return (f, g) if os.path.exists(f) and os.path.exists(g) else None
 
 
-def run_cpu_pipes(path, n_pipes):
-    """n_pipes x (fsk_demod --cs16 -s 2 921416 115177 file - | drs232_ldpc - -), all at once. -> (wall s, bytes out)"""
+def run_cpu_pipes(paths, n_pipes):
+    """n_pipes x (fsk_demod --cs16 -s 2 921416 115177 file - | drs232_ldpc - -), all at once, pipe i on paths[i % len].
+    -> (wall s, bytes out)"""
     f, g = ref_binaries()
-    cmd = "%s --cs16 -s 2 921416 115177 %s - 2>/dev/null | %s - - 2>/dev/null | wc -c" % (f, path, g)
+    cmd = "%s --cs16 -s 2 921416 115177 %s - 2>/dev/null | %s - - 2>/dev/null | wc -c"
     t0 = time.perf_counter()
-    procs = [subprocess.Popen(["bash", "-c", cmd], stdout=subprocess.PIPE, text=True) for _ in range(n_pipes)]
+    procs = [subprocess.Popen(["bash", "-c", cmd % (f, paths[i % len(paths)], g)], stdout=subprocess.PIPE, text=True)
+             for i in range(n_pipes)]
     outs = [p.communicate()[0] for p in procs]
     dt = time.perf_counter() - t0
     return dt, sum(int(o.strip() or 0) for o in outs)
@@ -159,15 +161,20 @@ def run_cpu_port(raw_cs16, n_threads):
 
 
 def cpu_sample_file(nsamp, tmpdir):
-    """cs16 file: a 10 dB v1 stream (the Eb/N0 of BASELINE.json configs[0]) tiled to nsamp samples"""
+    """cs16 files: one v1 stream per Eb/N0 of the GPU workload's 4-12 dB sweep (same generator, same clock offsets),
+    each tiled to nsamp samples; pipe i reads file i % 5"""
     from wenet_b200 import siggen
-    base, _ = siggen.make_stream(0, n_samples=1 << 20, ebno_db=10.0, fmt="cs16")
     reps = max(1, nsamp // (1 << 20))
-    path = os.path.join(tmpdir, "wb_cpu_sample.cs16")
-    with open(path, "wb") as fh:
-        for _ in range(reps):
-            fh.write(base.tobytes())
-    return path, reps * (1 << 20), base
+    paths, bases = [], []
+    for i, eb in enumerate(EBNO_SWEEP):
+        base, _ = siggen.make_stream(i, n_samples=1 << 20, ebno_db=eb, fmt="cs16", clock_ppm=float((i % 7 - 3) * 400))
+        path = os.path.join(tmpdir, "wb_cpu_sample_%d.cs16" % i)
+        with open(path, "wb") as fh:
+            for _ in range(reps):
+                fh.write(base.tobytes())
+        paths.append(path)
+        bases.append(base)
+    return paths, reps * (1 << 20), bases
 
 
 def cpu_baseline(nsamp_per_pipe, reps=1):
@@ -184,12 +191,12 @@ def cpu_baseline(nsamp_per_pipe, reps=1):
             used = min(cores, 2 * pipes)
         else:
             kind, pipes = "port", max(1, cores)
-            raw = np.tile(base, ns // (1 << 20))
+            raw = np.tile(base[3], ns // (1 << 20))
             best, nb = run_cpu_port(raw, pipes)
             used = pipes
         return {"value": round(pipes * ns / best / 1e6, 3), "unit": UNIT, "cores": used, "kind": kind,
-                "sample": "%d parallel pipes (fsk_demod --cs16 -s 2 921416 115177 | drs232_ldpc) x %d samples of a 10 dB "
-                          "v1 stream each, %.2f s wall, %d B decoded" % (pipes, ns, best, nb)}
+                "sample": "%d parallel pipes (fsk_demod --cs16 -s 2 921416 115177 | drs232_ldpc) x %d samples each, v1 streams "
+                          "at the workload's Eb/N0 sweep 4-12 dB, %.2f s wall, %d B decoded" % (pipes, ns, best, nb)}
     finally:
         shutil.rmtree(tmpdir, ignore_errors=True)
 
@@ -204,7 +211,7 @@ def reference_arm(args, rank, world):
         path, ns, base = cpu_sample_file(args.cpu_samples, tmpdir)
         have = ref_binaries() is not None
         pipes = max(1, cores // 2) if have else max(1, cores)
-        raw = None if have else np.tile(base, ns // (1 << 20))
+        raw = None if have else np.tile(base[3], ns // (1 << 20))
         times, nb = [], 0
         for i in range(args.warmup + args.steps):
             dt, nb = run_cpu_pipes(path, pipes) if have else run_cpu_port(raw, pipes)
@@ -219,7 +226,7 @@ def reference_arm(args, rank, world):
             "config": workload_config(args, world),
             "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": min(cores, 2 * pipes) if have else pipes,
                              "kind": "reference" if have else "port",
-                             "sample": "each step: %d parallel pipes x %d samples (10 dB v1 stream, cs16), %d B decoded per step"
+                             "sample": "each step: %d parallel pipes x %d samples (v1 streams at the Eb/N0 sweep 4-12 dB, cs16), %d B decoded per step"
                                        % (pipes, ns, nb)},
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -474,7 +481,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(8 << 20)
+        cpu = cpu_baseline(32 << 20)
 
     if rank == 0:
         line = {
