@@ -30,21 +30,26 @@
  *                      recurrence does not depend on the samples, so the W warps all run the same
  *                      chains and each mixes only its own segment of the frame (see the phase).
  *   B2 (stream warps, lane = block of Ts integrator outputs)  Ts-tap sums in the reference's
- *                      ring-buffer slot order, in place; |.|^2 summed over tones; the terms of the
- *                      fine-timing sum are formed here, in parallel.
- *   B3 (warp 0, lane = (re/im, stream))  the sequential fine-timing accumulation: only dependent
- *                      additions are left, in two half-frame passes; then atan2 / ppm / nin /
- *                      resampling offsets on the re-lanes.
- *   C  (stream warps, lanes = symbols)  linear-interpolated resampling and soft decisions,
- *                      48 (96) floats per frame written coalesced; next frame's cp.async.
+ *                      ring-buffer slot order, in place; e_i = |.|^2 summed over tones -> E.
+ *   B3 (warp 0 = real, warp 1 = imaginary part, lane = stream)  the sequential fine-timing
+ *                      accumulation t_c = sum e_i phi_ft[i]: one dependent addition per output,
+ *                      operands in loop-carried registers, the (periodic) multipliers in registers
+ *                      (wb_b3_chain).
+ *   C  (stream warps)  every lane recomputes the frame's scalars from t_c (atan2 timing estimate,
+ *                      ppm, next nin, resampling offsets); lanes = symbols: linear-interpolated
+ *                      resampling and soft decisions, 48 (96) floats per frame written coalesced;
+ *                      next frame's cp.async.
  *
  * The sequential phases cost a few warps' issue slots for ALL streams of the CTA (every lane carries
  * a different dependent chain); while one CTA of an SM is in B1/B3 the other one runs A/B2/C.
  *
  * Shared memory per stream: X[nst + nmax] float2 (the nst = 2Ts + Ts/2 old samples the mixer can reach
  * back to + the new ones -> tone 0 mixer products -> tone 0 integrator outputs, all in place),
- * Y[(M-1) * ylen] float2 for the other tones (the FFT work buffer in phase A) and E, half a frame of
- * fine-timing terms (re | im).
+ * Y[(M-1) * ylen] float2 for the other tones (the FFT work buffer in phase A) and E, the frame's
+ * fine-timing terms e_i.  The L1 that is left beside 228 KB of shared memory is flushed by the sample
+ * stream every frame: a global or local (spill) load is an L2 round trip and an indexed constant-bank
+ * load issues only every ~10 cycles, so the frame geometry is compile-time (BLK) and tables live in
+ * shared memory, registers or immediates wherever a sequential phase needs them.
  * Stream regions are an odd multiple of 8 bytes mod 128 apart so the lanes of warp 0 (one stream
  * each) hit distinct banks.  For Ts = 8 the mixer products / integrator outputs are stored with
  * their low three index bits XORed with bits 4..6 (wb_phys) so that B2's lanes, which walk blocks
