@@ -14,10 +14,12 @@ in HBM; every step demodulates a full chunk.  Multi-GPU: weak scaling, 4096 stre
 `value`  : whole-job Msamples/s with the chunk already resident in HBM (CUDA events on the engine's stream).
 `e2e`    : the same metric through the public API with HOST buffers: wb_feed_strided (pinned host -> HBM),
            wb_process, wb_sync, wb_drain_all_packets (HBM -> host) every step, wall clock around device syncs.
-           The host buffers hold the streams as cs16 -- the bytes the reference arm's `fsk_demod --cs16` reads
-           (the reference cannot read float IQ at all, src/fsk_demod.c:92-106) -- so both arms of the headline
-           ratio consume the same input; the same run with cf32 (8 B/sample over PCIe) and cu8 (2 B/sample,
-           the format of the reference's own benchmark) host buffers is reported beside it (e2e_cf32, e2e_cu8).
+           The host buffers hold the streams as cu8, 2 bytes per IQ sample: what rtl_sdr delivers to the
+           reference receiver (start_rx.sh:125, `fsk_demod --cu8`), what the reference's own benchmark pipes into it
+           (benchmarking/README.md: `csdr convert_f_u8 | fsk_demod --cu8`) and what this bench's reference arm reads
+           -- the reference cannot read float IQ at all (src/fsk_demod.c:92-106) -- so both arms of the headline
+           ratio consume the same bytes.  The same run with cs16 (4 B/sample) and cf32 (8 B/sample) host buffers is
+           reported beside it (e2e_cs16, e2e_cf32): all three are bound by the PCIe copy.
 `roofline`: the dominant kernel (wb_fsk_kernel): algorithmic bytes (8.5 B per IQ sample) / its
            event-timed duration, against the measured HBM peak in MEASURED_PEAKS.json.
 `cpu_baseline`: the reference's own binaries (oracle/_ref: fsk_demod | drs232_ldpc, built from the unmodified
@@ -131,10 +133,10 @@ def ref_binaries():
 
 
 def run_cpu_pipes(paths, n_pipes):
-    """n_pipes x (fsk_demod --cs16 -s 2 921416 115177 file - | drs232_ldpc - -), all at once, pipe i on paths[i % len].
+    """n_pipes x (fsk_demod --cu8 -s 2 921416 115177 file - | drs232_ldpc - -), all at once, pipe i on paths[i % len].
     -> (wall s, bytes out)"""
     f, g = ref_binaries()
-    cmd = "%s --cs16 -s 2 921416 115177 %s - 2>/dev/null | %s - - 2>/dev/null | wc -c"
+    cmd = "%s --cu8 -s 2 921416 115177 %s - 2>/dev/null | %s - - 2>/dev/null | wc -c"
     t0 = time.perf_counter()
     procs = [subprocess.Popen(["bash", "-c", cmd % (f, paths[i % len(paths)], g)], stdout=subprocess.PIPE, text=True)
              for i in range(n_pipes)]
@@ -143,14 +145,14 @@ def run_cpu_pipes(paths, n_pipes):
     return dt, sum(int(o.strip() or 0) for o in outs)
 
 
-def run_cpu_port(raw_cs16, n_threads):
+def run_cpu_port(raw_cu8, n_threads):
     """fallback when oracle/_ref is absent: the C restatement (oracle/liboracle.so), one stream per thread"""
     from oracle import oracle as O
     port = O.Oracle("port")
     nbytes = [0] * n_threads
 
     def work(i):
-        sd, _, _ = port.fsk(921416, 115177, M=2).run(raw_cs16, "cs16")
+        sd, _, _ = port.fsk(921416, 115177, M=2).run(raw_cu8, "cu8")
         nbytes[i] = len(port.deframer("v1", 10).feed(sd)["packets"])
 
     t0 = time.perf_counter()
@@ -161,20 +163,19 @@ def run_cpu_port(raw_cs16, n_threads):
 
 
 def cpu_sample_file(nsamp, tmpdir):
-    """cs16 files: one v1 stream per Eb/N0 of the GPU workload's 4-12 dB sweep (same generator, same clock offsets),
-    each tiled to nsamp samples; pipe i reads file i % 5"""
+    """cu8 file: five v1 streams, one per Eb/N0 of the GPU workload's 4-12 dB sweep (same generator, same clock offsets),
+    1 Mi samples each, back to back, tiled to about nsamp samples: every pipe does the same, balanced work"""
     from wenet_b200 import siggen
-    reps = max(1, nsamp // (1 << 20))
-    paths, bases = [], []
-    for i, eb in enumerate(EBNO_SWEEP):
-        base, _ = siggen.make_stream(i, n_samples=1 << 20, ebno_db=eb, fmt="cs16", clock_ppm=float((i % 7 - 3) * 400))
-        path = os.path.join(tmpdir, "wb_cpu_sample_%d.cs16" % i)
-        with open(path, "wb") as fh:
-            for _ in range(reps):
-                fh.write(base.tobytes())
-        paths.append(path)
-        bases.append(base)
-    return paths, reps * (1 << 20), bases
+    seg = [siggen.make_stream(i, n_samples=1 << 20, ebno_db=eb, fmt="cu8", clock_ppm=float((i % 7 - 3) * 400))[0]
+           for i, eb in enumerate(EBNO_SWEEP)]
+    base = np.concatenate(seg)
+    per = len(seg) << 20
+    reps = max(1, nsamp // per)
+    path = os.path.join(tmpdir, "wb_cpu_sample.cu8")
+    with open(path, "wb") as fh:
+        for _ in range(reps):
+            fh.write(base.tobytes())
+    return [path], reps * per, base
 
 
 def cpu_baseline(nsamp_per_pipe, reps=1):
@@ -191,12 +192,12 @@ def cpu_baseline(nsamp_per_pipe, reps=1):
             used = min(cores, 2 * pipes)
         else:
             kind, pipes = "port", max(1, cores)
-            raw = np.tile(base[3], ns // (1 << 20))
+            raw = np.tile(base, ns // (base.size // 2))
             best, nb = run_cpu_port(raw, pipes)
             used = pipes
         return {"value": round(pipes * ns / best / 1e6, 3), "unit": UNIT, "cores": used, "kind": kind,
-                "sample": "%d parallel pipes (fsk_demod --cs16 -s 2 921416 115177 | drs232_ldpc) x %d samples each, v1 streams "
-                          "at the workload's Eb/N0 sweep 4-12 dB, %.2f s wall, %d B decoded" % (pipes, ns, best, nb)}
+                "sample": "%d parallel pipes (fsk_demod --cu8 -s 2 921416 115177 | drs232_ldpc) x %d samples each (v1 streams at the "
+                          "workload's Eb/N0 sweep 4-12 dB back to back), %.2f s wall, %d B decoded" % (pipes, ns, best, nb)}
     finally:
         shutil.rmtree(tmpdir, ignore_errors=True)
 
@@ -211,7 +212,7 @@ def reference_arm(args, rank, world):
         path, ns, base = cpu_sample_file(args.cpu_samples, tmpdir)
         have = ref_binaries() is not None
         pipes = max(1, cores // 2) if have else max(1, cores)
-        raw = None if have else np.tile(base[3], ns // (1 << 20))
+        raw = None if have else np.tile(base, ns // (base.size // 2))
         times, nb = [], 0
         for i in range(args.warmup + args.steps):
             dt, nb = run_cpu_pipes(path, pipes) if have else run_cpu_port(raw, pipes)
@@ -226,7 +227,7 @@ def reference_arm(args, rank, world):
             "config": workload_config(args, world),
             "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": min(cores, 2 * pipes) if have else pipes,
                              "kind": "reference" if have else "port",
-                             "sample": "each step: %d parallel pipes x %d samples (v1 streams at the Eb/N0 sweep 4-12 dB, cs16), %d B decoded per step"
+                             "sample": "each step: %d parallel pipes x %d samples (v1 streams at the Eb/N0 sweep 4-12 dB back to back, cu8), %d B decoded per step"
                                        % (pipes, ns, nb)},
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -248,7 +249,7 @@ def workload_config(args, world):
             "streams_per_gpu": args.streams, "chunk_samples": args.chunk, "in_fmt": "cf32", "framing": "v1",
             "ldpc_max_iter": 10, "parallelism": "stream-sharded x%d, no collective" % world,
             "l2": "inputs (%.1f GB per step per GPU) larger than L2" % (args.streams * args.chunk * 8 / 1e9),
-            "e2e_in_fmt": "cs16 (the reference arm's input bytes)", "e2e_host_bytes_per_step": args.e2e_bytes,
+            "e2e_in_fmt": "cu8 (rtl_sdr's format = the reference arm's input bytes)", "e2e_host_bytes_per_step": args.e2e_bytes,
             "synth": args.synth}
 
 
@@ -472,12 +473,12 @@ def main():
         del pins
         return res
 
-    e2e = e2e_cf32 = e2e_cu8 = None
+    e2e = e2e_cf32 = e2e_cs16 = None
     if not args.no_e2e:
         eng.close()
-        e2e = run_e2e("cs16", 2)
+        e2e = run_e2e("cu8", 2)
+        e2e_cs16 = run_e2e("cs16", 2)
         e2e_cf32 = run_e2e("cf32", 2)
-        e2e_cu8 = run_e2e("cu8", 2)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -489,7 +490,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world),
-            "clocks": clk, "e2e": e2e, "e2e_cf32": e2e_cf32, "e2e_cu8": e2e_cu8, "gpu_launches": int(l1 - l0),
+            "clocks": clk, "e2e": e2e, "e2e_cs16": e2e_cs16, "e2e_cf32": e2e_cf32, "gpu_launches": int(l1 - l0),
             "roofline": roofline, "cpu_baseline": cpu,
             "work_per_step_per_gpu": {"samples": int(samples_step), "codewords": int(codewords_step),
                                       "crc_valid_packets": packets_last},
