@@ -459,3 +459,27 @@ def test_tx_noisy_round_trip(eng_mod, oracle_port):
         for s in range(n):
             assert e.drain_packets(s) == pl[s].tobytes(), (fmt, s)
         e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,P,fmt", [(siggen.V1, 4, "cf32"), (siggen.V1, 2, "cu8"), (siggen.V2, 5, "cs16")])
+def test_general_P_vs_oracle(eng_mod, oracle_port, cfg, P, fmt):
+    """fsk_demod -p P with P < Ts (reference src/fsk_demod.c:186-188, src/fsk.c:139): the kernel's general-geometry
+    instantiation (BLK = false) -- soft decisions, nin sequence, timing state and packets against the oracle"""
+    framing = "v1" if cfg is siggen.V1 else "v2"
+    raw, payloads = siggen.make_stream(31, n_packets=2, ebno_db=9.0, framing=framing, fmt=fmt, clock_ppm=-1500.0)
+    sd_o, log_o, cons_o, res_o = _run_oracle_stream(oracle_port, raw, fmt, cfg["Fs"], cfg["Rs"], 2, framing, P=P)
+    nsamp = raw.size // eng_mod.FMT_ELEMS[fmt]
+    e = eng_mod.Engine(1, Fs=cfg["Fs"], Rs=cfg["Rs"], P=P, in_fmt=fmt, framing=framing, chunk_samples=nsamp + 1024)
+    e.enable_frame_log(len(log_o) + 4)
+    e.feed([raw])
+    e.process()
+    e.sync()
+    sd_g = e.drain_soft(0)
+    log_g = e.read_frame_log(0, len(log_o))
+    assert np.array_equal(log_g[:, 0], log_o[:, 0]), "nin sequence"
+    assert np.array_equal(log_g[:, 5].view(np.uint32), log_o[:, 5].view(np.uint32)), "norm_rx_timing"
+    assert np.array_equal(log_g[:, 6].view(np.uint32), log_o[:, 6].view(np.uint32)), "ppm"
+    assert np.array_equal(sd_g.view(np.uint32), sd_o.view(np.uint32))
+    assert e.drain_packets(0) == res_o["packets"]
+    e.close()
