@@ -159,6 +159,24 @@ __device__ __forceinline__ void wb_cp_async_wait()
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
+/* Tensor memory as lane-private scratch: this kernel issues no MMA, so its 256 KB per SM sit idle, while the register
+   file is the scarcest resource here (72 registers per thread, and what spills goes to L2: the L1 is flushed by the
+   sample stream).  A warp may touch the 32 TMEM lanes of its quadrant (warp % 4); 32x32b accesses give every thread
+   one 32-bit cell per column, so a warp's private columns work like 8 extra registers per thread with a ~12-cycle
+   access.  The spectrum estimate (used only in phase A) and the carried-over samples (A -> C) wait there. */
+__device__ __forceinline__ void wb_tmem_st8(unsigned taddr, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+                 "tcgen05.wait::st.sync.aligned;"
+                 :: "r"(taddr), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4), "f"(a5), "f"(a6), "f"(a7) : "memory");
+}
+__device__ __forceinline__ void wb_tmem_ld8(unsigned taddr, float &a0, float &a1, float &a2, float &a3, float &a4, float &a5, float &a6, float &a7)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3), "=f"(a4), "=f"(a5), "=f"(a6), "=f"(a7) : "r"(taddr) : "memory");
+}
+
 /* FFT work buffer index: XOR bits 4..5 into both bit pairs below them.  The leaf stores (lanes differ in bits
    2..5), the radix-4 level with m = 4 (lanes differ in bits 0..1 and 4..5) and the wider levels (lanes differ
    in bits 0..3) all become bank-conflict free. */
@@ -327,6 +345,18 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     float2 stash = make_float2(0.0f, 0.0f);
 #pragma unroll
     for (int q = 0; q < WB_NEQ; q++) est[q] = 0.0f;
+    /* 32 TMEM columns per CTA: 8 per warp, warps of one quadrant side by side */
+    static_assert(WB_NEQ == 4, "est[4] + stash fill one 8-column TMEM row");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;\n"
+                     "tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;"
+                     :: "r"((unsigned)__cvta_generic_to_shared(&sc[0].pad1)) : "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_base = (unsigned)sc[0].pad1;
+    const unsigned taddr = tmem_base + ((unsigned)(32 * (warp & 3)) << 16) + 8u * (unsigned)(warp >> 2);
     for (int i = tid; i < 3 * (Ndft >> 2); i += blockDim.x) TW[i] = __ldg(&p.tw[i]);
     if (have) {
         pos = (unsigned)st->in_pos; fill = (unsigned)st->in_fill; nin = st->nin;
@@ -360,6 +390,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             else if (n_ < NMAX) xd_[n_] = make_float2(0.0f, 0.0f);                                    \
         }                                                                                               \
     } while (0)
+    wb_tmem_st8(taddr, est[0], est[1], est[2], est[3], 0.0f, 0.0f, 0.0f, 0.0f);
     if (CF32 && have) WB_FETCH_CF32(pos);
 
     const float omt = __fsub_rn(1.0f, p.tc);
@@ -377,6 +408,10 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 
         /* ================= A: stream warps ================= */
         if (active) {
+            {
+                float d0, d1, d2, d3;
+                wb_tmem_ld8(taddr, est[0], est[1], est[2], est[3], d0, d1, d2, d3);
+            }
             /* the leaf butterflies' table entries first: their latency hides behind the landing of the frame */
             constexpr int pp0 = 4, istr = Ndft / pp0;            /* 256 = 4 x 4 x 4 x 4, reference src/kiss_fft.c:311-338 */
             const int nwin = min(nin - Ndft, Ndft);
@@ -557,6 +592,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             /* the samples the next frame's mixer reaches back to (reference src/fsk.c:851 keeps 4 Ts, uses at most
                2 Ts + Ts/2) sit where the mixer products are about to land: lift them into registers */
             if (lane < nst) stash = X[nin + lane];
+            wb_tmem_st8(taddr, est[0], est[1], est[2], est[3], stash.x, stash.y, 0.0f, 0.0f);
             if (lane == 0) {
                 wb_fsk_sc &c = sc[warp];
                 const bool first = c.pb[0] == 0;         /* fsk->f_est[0] < 1, reference src/fsk.c:729 */
@@ -929,6 +965,10 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             }
             __syncwarp();
             /* old samples for the next frame */
+            {
+                float e0, e1, e2, e3, d2, d3;
+                wb_tmem_ld8(taddr, e0, e1, e2, e3, stash.x, stash.y, d2, d3);
+            }
             if (lane < nst) X[lane] = stash;
             /* the integrator outputs in X are consumed: send the next frame's samples on their way */
             if (CF32) {
@@ -953,6 +993,14 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     }
 
     /* ---- write the state back ---- */
+    {
+        float d0, d1, d2, d3;
+        wb_tmem_ld8(taddr, est[0], est[1], est[2], est[3], d0, d1, d2, d3);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" :: "r"(tmem_base) : "memory");
     if (have) {
         const wb_fsk_sc &c = sc[warp];
 #pragma unroll
