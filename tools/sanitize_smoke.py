@@ -3,7 +3,10 @@
 import sys
 import numpy as np
 sys.path.insert(0, '.')
+import os
 from wenet_b200 import engine as E, siggen
+if os.environ.get("WB_LIB"):            # e.g. the `san` build (no tensor-memory scratch) for synccheck
+    E._lib = E.load_library(os.path.abspath(os.environ["WB_LIB"]))
 
 def run(label, raws, **kw):
     e = E.Engine(len(raws), chunk_samples=1 << 17, stats=True, **kw)

@@ -345,6 +345,9 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     float2 stash = make_float2(0.0f, 0.0f);
 #pragma unroll
     for (int q = 0; q < WB_NEQ; q++) est[q] = 0.0f;
+    /* (-DWB_NO_TMEM, the `san` build of the Makefile, keeps these values in registers instead: compute-sanitizer's
+       synccheck mistakes tcgen05.alloc for an uninitialised mbarrier and stops the kernel) */
+#ifndef WB_NO_TMEM
     /* 32 TMEM columns per CTA: 8 per warp, warps of one quadrant side by side */
     static_assert(WB_NEQ == 4, "est[4] + stash fill one 8-column TMEM row");
     if (warp == 0) {
@@ -357,6 +360,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem_base = (unsigned)sc[0].pad1;
     const unsigned taddr = tmem_base + ((unsigned)(32 * (warp & 3)) << 16) + 8u * (unsigned)(warp >> 2);
+#endif
     for (int i = tid; i < 3 * (Ndft >> 2); i += blockDim.x) TW[i] = __ldg(&p.tw[i]);
     if (have) {
         pos = (unsigned)st->in_pos; fill = (unsigned)st->in_fill; nin = st->nin;
@@ -390,7 +394,9 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             else if (n_ < NMAX) xd_[n_] = make_float2(0.0f, 0.0f);                                    \
         }                                                                                               \
     } while (0)
+#ifndef WB_NO_TMEM
     wb_tmem_st8(taddr, est[0], est[1], est[2], est[3], 0.0f, 0.0f, 0.0f, 0.0f);
+#endif
     if (CF32 && have) WB_FETCH_CF32(pos);
 
     const float omt = __fsub_rn(1.0f, p.tc);
@@ -408,10 +414,12 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 
         /* ================= A: stream warps ================= */
         if (active) {
+#ifndef WB_NO_TMEM
             {
                 float d0, d1, d2, d3;
                 wb_tmem_ld8(taddr, est[0], est[1], est[2], est[3], d0, d1, d2, d3);
             }
+#endif
             /* the leaf butterflies' table entries first: their latency hides behind the landing of the frame */
             constexpr int pp0 = 4, istr = Ndft / pp0;            /* 256 = 4 x 4 x 4 x 4, reference src/kiss_fft.c:311-338 */
             const int nwin = min(nin - Ndft, Ndft);
@@ -592,7 +600,9 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             /* the samples the next frame's mixer reaches back to (reference src/fsk.c:851 keeps 4 Ts, uses at most
                2 Ts + Ts/2) sit where the mixer products are about to land: lift them into registers */
             if (lane < nst) stash = X[nin + lane];
+#ifndef WB_NO_TMEM
             wb_tmem_st8(taddr, est[0], est[1], est[2], est[3], stash.x, stash.y, 0.0f, 0.0f);
+#endif
             if (lane == 0) {
                 wb_fsk_sc &c = sc[warp];
                 const bool first = c.pb[0] == 0;         /* fsk->f_est[0] < 1, reference src/fsk.c:729 */
@@ -965,10 +975,12 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             }
             __syncwarp();
             /* old samples for the next frame */
+#ifndef WB_NO_TMEM
             {
                 float e0, e1, e2, e3, d2, d3;
                 wb_tmem_ld8(taddr, e0, e1, e2, e3, stash.x, stash.y, d2, d3);
             }
+#endif
             if (lane < nst) X[lane] = stash;
             /* the integrator outputs in X are consumed: send the next frame's samples on their way */
             if (CF32) {
@@ -993,6 +1005,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     }
 
     /* ---- write the state back ---- */
+#ifndef WB_NO_TMEM
     {
         float d0, d1, d2, d3;
         wb_tmem_ld8(taddr, est[0], est[1], est[2], est[3], d0, d1, d2, d3);
@@ -1001,6 +1014,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" :: "r"(tmem_base) : "memory");
+#endif
     if (have) {
         const wb_fsk_sc &c = sc[warp];
 #pragma unroll
