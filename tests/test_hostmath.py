@@ -88,3 +88,13 @@ def test_fine_timing_oscillator_is_periodic(hm, P, Rs):
     assert np.array_equal(re[(nt + 1) * P:].view(np.uint32), re[nt * P:-P].view(np.uint32))
     assert np.array_equal(im[(nt + 1) * P:].view(np.uint32), im[nt * P:-P].view(np.uint32))
     assert not np.array_equal(re[P:2 * P].view(np.uint32), re[:P].view(np.uint32))      # the transient is real
+
+
+def test_division_shortcuts(hm):
+    """the kernel multiplies by 1/(2 pi) and 1/48 where the reference divides (src/fsk.c:883,888: norm_rx_timing and the
+    ppm update): identical floats for every argument those divisions can ever see, checked exhaustively (2 x 10^9 floats)"""
+    hm.wbh_check_div_2pi.restype = C.c_long
+    hm.wbh_check_div_48.restype = C.c_long
+    assert hm.wbh_check_div_2pi() == 0
+    assert hm.wbh_check_div_48() == 0
+

@@ -879,11 +879,17 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             int nin_next = nin, low = 0, high = 0;
             float fract = 0.0f, norm = norm_old, ppm = ppm_old, rx_timing = 0.0f;
             if (!nan) {
-                norm = (float)((double)wb_atan2f(tci, tcr) / 6.283185307179586);
+                /* reference: atan2f(..) / (2 * M_PI), a double division rounded to float.  Multiplying by the double
+                   nearest to 1/(2 pi) gives the same float for EVERY float in [-3.2, 3.2] (checked exhaustively,
+                   tests/test_hostmath.py::test_division_shortcuts) and takes the division routine off the chain
+                   every stream warp waits on at the start of this phase */
+                norm = (float)((double)wb_atan2f(tci, tcr) * WB_INV_2PI);
                 rx_timing = __fmul_rn(norm, (float)Pc);
                 const float dn = __fsub_rn(norm, norm_old);
                 if ((double)fabsf(dn) < .2) {
-                    const float appm = (float)(1e6 * (double)dn / (double)(float)NSYM);
+                    /* 1e6 * dn / Nsym with Nsym = 48: the same float from a multiplication for every |dn| < 0.2 (same test) */
+                    static_assert(NSYM == 48, "WB_INV_48");
+                    const float appm = (float)((1e6 * (double)dn) * WB_INV_48);
                     ppm = (float)(.9 * (double)ppm_old + .1 * (double)appm);
                 }
                 if ((double)norm > 0.25) nin_next = N_ + TS / 2;

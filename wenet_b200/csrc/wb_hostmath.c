@@ -80,3 +80,47 @@ void wbh_pft_table(int P, int Rs, int n, float *re, float *im)
         pr = nr; pi_ = ni;
     }
 }
+
+/* the two double divisions of the per-frame scalars (reference src/fsk.c:883,888) against the multiplications the
+   kernel uses: number of floats for which they differ, over EVERY float the division can see */
+#include <string.h>
+long wbh_check_div_2pi(void)
+{
+    const double c = 6.283185307179586;        /* 2 * M_PI */
+    float top = 3.2f;                          /* |atan2f| <= pi */
+    uint32_t utop, u;
+    long bad = 0;
+    memcpy(&utop, &top, 4);
+    for (u = 0; u <= utop; u++) {
+        float a, q1, q2;
+        memcpy(&a, &u, 4);
+        q1 = (float)((double)a / c);
+        q2 = (float)((double)a * WB_INV_2PI);
+        if (memcmp(&q1, &q2, 4)) bad++;
+        q1 = (float)((double)-a / c);
+        q2 = (float)((double)-a * WB_INV_2PI);
+        if (memcmp(&q1, &q2, 4)) bad++;
+    }
+    return bad;
+}
+long wbh_check_div_48(void)
+{
+    float top = 0.2f;                          /* the ppm update is gated by |dn| < .2 */
+    uint32_t utop, u;
+    long bad = 0;
+    memcpy(&utop, &top, 4);
+    for (u = 0; u <= utop; u++) {
+        float a, q1, q2;
+        double t;
+        memcpy(&a, &u, 4);
+        t = 1e6 * (double)a;
+        q1 = (float)(t / (double)(float)48);
+        q2 = (float)(t * WB_INV_48);
+        if (memcmp(&q1, &q2, 4)) bad++;
+        q1 = (float)(-t / (double)(float)48);
+        q2 = (float)(-t * WB_INV_48);
+        if (memcmp(&q1, &q2, 4)) bad++;
+    }
+    return bad;
+}
+

@@ -360,4 +360,9 @@ WB_HD float wb_llr_scale(double four_esn0, float sd)
     }
 }
 
+/* reciprocals that replace two double divisions of the frame-scalar chain (exhaustively checked over every float
+   the divisions can see: wbh_check_div_2pi / wbh_check_div_48 in wb_hostmath.c) */
+#define WB_INV_2PI 0.15915494309189535      /* the double nearest to 1 / 6.283185307179586 */
+#define WB_INV_48  (1.0 / 48.0)
+
 #endif /* WB_MATH_H */
