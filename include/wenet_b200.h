@@ -39,6 +39,7 @@ extern "C" {
 
 #define WB_FLAG_KEEP_LLR   1u  /* keep per-codeword LLRs for wb_drain_codewords (test tap) */
 #define WB_FLAG_STATS      2u  /* compute the Eb/N0 + eye-diagram statistics every frame   */
+#define WB_FLAG_HARD_BITS  4u  /* also keep the demodulator's hard bits for wb_drain_hard      */
 
 #define WB_OK        0
 #define WB_EINVAL   -1   /* bad argument / unsupported configuration */
@@ -126,6 +127,10 @@ int  wb_drain_packets(wb_engine *e, int stream, uint8_t *buf, size_t cap, size_t
 int  wb_drain_all_packets(wb_engine *e, uint8_t *buf, size_t cap, size_t *nbytes, uint64_t *npackets);
 /* the fwrite(sdbuf) of fsk_demod.c:403: soft decisions of `stream` produced by the LAST wb_process */
 int  wb_drain_soft(wb_engine *e, int stream, float *buf, size_t cap_floats, size_t *n);
+/* the fwrite(bitbuf) of fsk_demod.c:405 (fsk_demod without -s): rx_bits of fsk_demod() (src/fsk.h:183,
+   src/fsk.c:936-959), one byte per bit, of `stream` from the LAST wb_process.  These are the arg-max tone
+   decisions, which for 4-FSK are not the signs of the soft decisions.  Needs WB_FLAG_HARD_BITS. */
+int  wb_drain_hard(wb_engine *e, int stream, uint8_t *buf, size_t cap, size_t *n);
 /* test tap: all codewords decoded by the LAST wb_process (CRC-valid or not), sorted by (stream, seq);
    llr (may be NULL; needs WB_FLAG_KEEP_LLR) receives 2580 floats per codeword */
 int  wb_drain_codewords(wb_engine *e, wb_codeword *cw, float *llr, size_t cap, size_t *n);

@@ -78,6 +78,9 @@ class Oracle:
         f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.POINTER(C.c_long),
                       C.c_void_p, C.c_long, C.POINTER(C.c_long)]
         f.restype = C.c_long
+        f = getattr(L, pre + "fsk_run_bits")
+        f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.POINTER(C.c_long)]
+        f.restype = C.c_long
         if kind == "port":
             L.wo_fsk_demod.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]; L.wo_fsk_demod.restype = None
             L.wo_crc16.argtypes = [C.c_void_p, C.c_int]; L.wo_crc16.restype = C.c_uint16
@@ -183,8 +186,8 @@ class _Fsk:
     def nin(self):
         return getattr(self.L, self.pre + "fsk_nin")(self.h)
 
-    def run(self, raw, fmt="cf32"):
-        """Frame loop over a whole stream -> (sd float32[], frame_log float32[frames][8], consumed)."""
+    @staticmethod
+    def _samples(raw, fmt):
         raw = np.ascontiguousarray(raw)
         if fmt == "cf32":
             raw = raw.view(np.float32) if raw.dtype == np.complex64 else raw.astype(np.float32)
@@ -195,6 +198,11 @@ class _Fsk:
             assert raw.dtype == np.int16; nsamp = raw.size // 2
         else:
             assert raw.dtype == np.int16; nsamp = raw.size
+        return raw, nsamp
+
+    def run(self, raw, fmt="cf32"):
+        """Frame loop over a whole stream -> (sd float32[], frame_log float32[frames][8], consumed)."""
+        raw, nsamp = self._samples(raw, fmt)
         max_frames = nsamp // 300 + 2
         sd = np.zeros(max_frames * self.nbits, dtype=np.float32)
         log = np.zeros((max_frames, 8), dtype=np.float32)
@@ -202,6 +210,14 @@ class _Fsk:
         nf = getattr(self.L, self.pre + "fsk_run")(self.h, FMT[fmt], _p(raw), nsamp, _p(sd), sd.size,
                                                   C.byref(n_sd), _p(log), max_frames, C.byref(cons))
         return sd[:n_sd.value].copy(), log[:nf].copy(), cons.value
+
+    def run_bits(self, raw, fmt="cf32"):
+        """The same frame loop through fsk_demod(): the hard bits `fsk_demod` writes without -s, one byte each."""
+        raw, nsamp = self._samples(raw, fmt)
+        bits = np.zeros((nsamp // 300 + 2) * self.nbits, dtype=np.uint8)
+        n = C.c_long(0)
+        getattr(self.L, self.pre + "fsk_run_bits")(self.h, FMT[fmt], _p(raw), nsamp, _p(bits), bits.size, C.byref(n))
+        return bits[:n.value].copy()
 
     def state(self):
         s = np.zeros(19, dtype=np.float32)

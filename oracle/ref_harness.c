@@ -167,6 +167,34 @@ void ref_fsk_eye(void *h, int *neyetr, int *neyesamp, float *out)
             out[i * st.neyesamp + j] = st.rx_eye[i][j];
 }
 
+/* sample conversion of one frame, the arithmetic of src/fsk_demod.c:273-296 */
+static void load_frame(COMP *modbuf, int fmt, const void *raw, long pos, int nin)
+{
+    int i;
+    if (fmt == 0) {
+        const float *p = (const float *)raw + 2 * pos;
+        for (i = 0; i < nin; i++) { modbuf[i].real = p[2 * i]; modbuf[i].imag = p[2 * i + 1]; }
+    } else if (fmt == 1) {
+        const uint8_t *p = (const uint8_t *)raw + 2 * pos;
+        for (i = 0; i < nin; i++) {
+            modbuf[i].real = ((float)p[2 * i] - 127.0) / 128.0;
+            modbuf[i].imag = ((float)p[2 * i + 1] - 127.0) / 128.0;
+        }
+    } else if (fmt == 2) {
+        const int16_t *p = (const int16_t *)raw + 2 * pos;
+        for (i = 0; i < nin; i++) {
+            modbuf[i].real = ((float)p[2 * i]) / FDMDV_SCALE;
+            modbuf[i].imag = ((float)p[2 * i + 1] / FDMDV_SCALE);
+        }
+    } else {
+        const int16_t *p = (const int16_t *)raw + pos;
+        for (i = 0; i < nin; i++) {
+            modbuf[i].real = ((float)p[i]) / FDMDV_SCALE;
+            modbuf[i].imag = 0.0;
+        }
+    }
+}
+
 /*
  * The frame loop of src/fsk_demod.c:270-299 over an in-memory stream.
  *   fmt: 0 = cf32 (test tap: samples are used as they are), 1 = cu8,
@@ -186,32 +214,10 @@ long ref_fsk_run(void *h, int fmt, const void *raw, long nsamp,
     int nmax = f->N + 2 * f->Ts;
     COMP *modbuf = (COMP *)malloc(sizeof(COMP) * (size_t)nmax);
     float *sdbuf = (float *)malloc(sizeof(float) * (size_t)f->Nbits);
-    int i;
     memset(sdbuf, 0, sizeof(float) * (size_t)f->Nbits);
     while (pos + (long)fsk_nin(f) <= nsamp) {
         int nin = (int)fsk_nin(f);
-        if (fmt == 0) {
-            const float *p = (const float *)raw + 2 * pos;
-            for (i = 0; i < nin; i++) { modbuf[i].real = p[2 * i]; modbuf[i].imag = p[2 * i + 1]; }
-        } else if (fmt == 1) {
-            const uint8_t *p = (const uint8_t *)raw + 2 * pos;
-            for (i = 0; i < nin; i++) {
-                modbuf[i].real = ((float)p[2 * i] - 127.0) / 128.0;
-                modbuf[i].imag = ((float)p[2 * i + 1] - 127.0) / 128.0;
-            }
-        } else if (fmt == 2) {
-            const int16_t *p = (const int16_t *)raw + 2 * pos;
-            for (i = 0; i < nin; i++) {
-                modbuf[i].real = ((float)p[2 * i]) / FDMDV_SCALE;
-                modbuf[i].imag = ((float)p[2 * i + 1] / FDMDV_SCALE);
-            }
-        } else {
-            const int16_t *p = (const int16_t *)raw + pos;
-            for (i = 0; i < nin; i++) {
-                modbuf[i].real = ((float)p[i]) / FDMDV_SCALE;
-                modbuf[i].imag = 0.0;
-            }
-        }
+        load_frame(modbuf, fmt, raw, pos, nin);
         fsk_demod_sd(f, sdbuf, modbuf);
         pos += nin;
         if (nsd + f->Nbits <= sd_cap) {
@@ -230,6 +236,27 @@ long ref_fsk_run(void *h, int fmt, const void *raw, long nsamp,
     free(sdbuf);
     *n_sd = nsd;
     *consumed = pos;
+    return frames;
+}
+
+/* The same loop through fsk_demod() (fsk_demod without -s, src/fsk_demod.c:301,405): hard bits, one byte each */
+long ref_fsk_run_bits(void *h, int fmt, const void *raw, long nsamp, uint8_t *bits_out, long cap, long *n_bits)
+{
+    struct FSK *f = (struct FSK *)h;
+    long pos = 0, frames = 0, nb = 0;
+    COMP *modbuf = (COMP *)malloc(sizeof(COMP) * (size_t)(f->N + 2 * f->Ts));
+    uint8_t *bitbuf = (uint8_t *)calloc((size_t)f->Nbits, 1);
+    while (pos + (long)fsk_nin(f) <= nsamp) {
+        int nin = (int)fsk_nin(f);
+        load_frame(modbuf, fmt, raw, pos, nin);
+        fsk_demod(f, bitbuf, modbuf);
+        pos += nin;
+        if (nb + f->Nbits <= cap) { memcpy(bits_out + nb, bitbuf, (size_t)f->Nbits); nb += f->Nbits; }
+        frames++;
+    }
+    free(modbuf);
+    free(bitbuf);
+    *n_bits = nb;
     return frames;
 }
 

@@ -746,29 +746,36 @@ void wo_fsk_eye(wo_fsk *f, int *neyetr, int *neyesamp, float *out)
         for (j = 0; j < f->neyesamp; j++) out[i * f->neyesamp + j] = f->rx_eye[i][j];
 }
 
+/* sample conversion of one frame, reference src/fsk_demod.c:273-296 */
+static void load_frame(float *mod, int fmt, const void *raw, long pos, int nin)
+{
+    int i;
+    if (fmt == 0) {
+        memcpy(mod, (const float *)raw + 2 * pos, sizeof(float) * 2 * (size_t)nin);
+    } else if (fmt == 1) {
+        const uint8_t *p = (const uint8_t *)raw + 2 * pos;
+        for (i = 0; i < 2 * nin; i++) mod[i] = (float)(((float)p[i] - 127.0) / 128.0);
+    } else if (fmt == 2) {
+        const int16_t *p = (const int16_t *)raw + 2 * pos;
+        for (i = 0; i < 2 * nin; i++) mod[i] = ((float)p[i]) / 1000;
+    } else {
+        const int16_t *p = (const int16_t *)raw + pos;
+        for (i = 0; i < nin; i++) { mod[2 * i] = ((float)p[i]) / 1000; mod[2 * i + 1] = 0.0f; }
+    }
+}
+
 /* frame loop + input conversion, reference src/fsk_demod.c:270-299, :403-412 */
 long wo_fsk_run(wo_fsk *f, int fmt, const void *raw, long nsamp,
                 float *sd_out, long sd_cap, long *n_sd,
                 float *frame_log, long log_cap, long *consumed)
 {
     long pos = 0, frames = 0, nsd = 0;
-    int nmax = f->N + 2 * f->Ts, i;
+    int nmax = f->N + 2 * f->Ts;
     float *mod = (float *)malloc(sizeof(float) * 2 * (size_t)nmax);
     float *sdbuf = (float *)calloc((size_t)f->Nbits, sizeof(float));
     while (pos + f->nin <= nsamp) {
         int nin = f->nin;
-        if (fmt == 0) {
-            memcpy(mod, (const float *)raw + 2 * pos, sizeof(float) * 2 * (size_t)nin);
-        } else if (fmt == 1) {
-            const uint8_t *p = (const uint8_t *)raw + 2 * pos;
-            for (i = 0; i < 2 * nin; i++) mod[i] = (float)(((float)p[i] - 127.0) / 128.0);
-        } else if (fmt == 2) {
-            const int16_t *p = (const int16_t *)raw + 2 * pos;
-            for (i = 0; i < 2 * nin; i++) mod[i] = ((float)p[i]) / 1000;
-        } else {
-            const int16_t *p = (const int16_t *)raw + pos;
-            for (i = 0; i < nin; i++) { mod[2 * i] = ((float)p[i]) / 1000; mod[2 * i + 1] = 0.0f; }
-        }
+        load_frame(mod, fmt, raw, pos, nin);
         wo_fsk_demod(f, sdbuf, NULL, mod);
         pos += nin;
         if (nsd + f->Nbits <= sd_cap) {
@@ -785,6 +792,25 @@ long wo_fsk_run(wo_fsk *f, int fmt, const void *raw, long nsamp,
     }
     free(mod); free(sdbuf);
     *n_sd = nsd; *consumed = pos;
+    return frames;
+}
+
+/* the same loop with the hard bits of fsk_demod() (fsk_demod without -s: src/fsk_demod.c:301, :405), one byte each */
+long wo_fsk_run_bits(wo_fsk *f, int fmt, const void *raw, long nsamp, uint8_t *bits_out, long cap, long *n_bits)
+{
+    long pos = 0, frames = 0, nb = 0;
+    float *mod = (float *)malloc(sizeof(float) * 2 * (size_t)(f->N + 2 * f->Ts));
+    uint8_t *bitbuf = (uint8_t *)calloc((size_t)f->Nbits, 1);
+    while (pos + f->nin <= nsamp) {
+        int nin = f->nin;
+        load_frame(mod, fmt, raw, pos, nin);
+        wo_fsk_demod(f, NULL, bitbuf, mod);
+        pos += nin;
+        if (nb + f->Nbits <= cap) { memcpy(bits_out + nb, bitbuf, (size_t)f->Nbits); nb += f->Nbits; }
+        frames++;
+    }
+    free(mod); free(bitbuf);
+    *n_bits = nb;
     return frames;
 }
 

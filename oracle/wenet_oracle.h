@@ -80,6 +80,8 @@ void wo_fsk_eye(wo_fsk *f, int *neyetr, int *neyesamp, float *out);
 long wo_fsk_run(wo_fsk *f, int fmt, const void *raw, long nsamp,
                 float *sd_out, long sd_cap, long *n_sd,
                 float *frame_log, long log_cap, long *consumed);
+/* the same loop through the hard-decision output of fsk_demod() (src/fsk.c:936-959): one byte per bit */
+long wo_fsk_run_bits(wo_fsk *f, int fmt, const void *raw, long nsamp, uint8_t *bits_out, long cap, long *n_bits);
 
 /* ---- transmit side ---- */
 /* one on-air frame (preamble + unique word + body) as 0/1 bytes in transmit order: reference tx/PacketTX.py:123-137,

@@ -71,6 +71,17 @@ def test_fsk_4fsk_stream(oracle_port):
     assert best > 0.99
 
 
+def test_fsk_hard_bits(oracle_port):
+    """fsk_demod without -s: the arg-max tone decisions of src/fsk.c:936-959, the reference CLI's own bytes"""
+    z = g("fsk_hard.npz")
+    b4 = oracle_port.fsk(921416, 115177, M=4).run_bits(z["raw4"], "cu8")
+    assert np.array_equal(b4, z["bits4"])
+    sd4, _, _ = oracle_port.fsk(921416, 115177, M=4).run(z["raw4"], "cu8")
+    assert np.mean((sd4 > 0) != z["bits4"]) > 0.01      # they are NOT the signs of the 4-FSK soft decisions
+    b2 = oracle_port.fsk(921416, 115177, M=2).run_bits(z["raw2"], "cs16")
+    assert np.array_equal(b2, z["bits2"])
+
+
 def test_tx_side(oracle_port):
     """transmit side: the modulator restatement against the reference's fsk_mod_c output, the frame
     builder against frames the reference receiver accepted, the scramble table against tx/radio_wrappers.py's"""

@@ -220,6 +220,67 @@ def test_4fsk_soft_vs_oracle(eng_mod, oracle_port):
     e.close()
 
 
+@pytest.mark.parametrize("M,fmt,Fs,Rs", [(4, "cf32", 921416, 115177), (4, "cu8", 921416, 115177),
+                                         (2, "cs16", 921416, 115177), (2, "cf32", 960000, 96000)])
+def test_hard_bits_vs_oracle(eng_mod, oracle_port, M, fmt, Fs, Rs):
+    """WB_FLAG_HARD_BITS / wb_drain_hard: rx_bits of fsk_demod() (reference src/fsk.c:936-959, what `fsk_demod` writes
+    without -s) next to unchanged soft decisions, fed in uneven pieces so that frames straddle process() calls"""
+    raws = []
+    for s in range(3):
+        if M == 4:
+            raw, _ = siggen.make_4fsk_stream(80 + s, 3000, ebno_db=4.0 + 3 * s, fmt=fmt)
+        else:
+            raw, _ = siggen.make_stream(80 + s, n_packets=1, ebno_db=3.0 + 3 * s, fmt=fmt, clock_ppm=2000.0 * (s - 1),
+                                        framing="v1" if Fs == 921416 else "v2")
+        raws.append(raw)
+    per = 2 if fmt != "s16" else 1
+    nmin = min(r.size for r in raws) // per
+    raws = [r[:nmin * per] for r in raws]
+    refs_b = [oracle_port.fsk(Fs, Rs, M=M).run_bits(r, fmt) for r in raws]
+    refs_s = [oracle_port.fsk(Fs, Rs, M=M).run(r, fmt)[0] for r in raws]
+    e = eng_mod.Engine(3, Fs=Fs, Rs=Rs, M=M, in_fmt=fmt, framing="none", chunk_samples=nmin // 3 + 2048, hard_bits=True)
+    got_b, got_s = [[] for _ in raws], [[] for _ in raws]
+    cuts = [0, nmin // 3 - 77, 2 * nmin // 3 + 131, nmin]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        e.feed([r[a * per:b * per] for r in raws])
+        e.process()
+        e.sync()
+        for s in range(3):
+            got_b[s].append(e.drain_hard(s))
+            got_s[s].append(e.drain_soft(s))
+    for s in range(3):
+        hb, sd = np.concatenate(got_b[s]), np.concatenate(got_s[s])
+        assert hb.size == refs_b[s].size > 1000 and np.array_equal(hb, refs_b[s]), s
+        assert np.array_equal(sd.view(np.uint32), refs_s[s].view(np.uint32)), s
+    if M == 4:      # the arg-max decisions are not the signs of the 4-FSK soft decisions
+        assert any(np.any((np.concatenate(got_s[s]) > 0) != np.concatenate(got_b[s])) for s in range(3))
+    e.close()
+    # without the flag the tap refuses instead of returning stale bytes
+    e = eng_mod.Engine(1, Fs=Fs, Rs=Rs, M=M, in_fmt=fmt, framing="none", chunk_samples=4096)
+    with pytest.raises(eng_mod.WbError):
+        e.drain_hard(0)
+    e.close()
+
+
+def test_hard_bits_golden_and_cli(eng_mod):
+    """the reference CLI's own hard-bit bytes (tests/golden/fsk_hard.npz) through the engine and through the
+    `fsk_demod` stand-in without -s"""
+    import subprocess
+    import sys
+    z = np.load(os.path.join(GOLD, "fsk_hard.npz"))
+    for M, fmt, raw, bits in ((4, "cu8", z["raw4"], z["bits4"]), (2, "cs16", z["raw2"], z["bits2"])):
+        e = eng_mod.Engine(1, M=M, in_fmt=fmt, framing="none", chunk_samples=raw.size // 2 + 1024, hard_bits=True)
+        e.feed([raw])
+        e.process()
+        e.sync()
+        assert np.array_equal(e.drain_hard(0), bits), M
+        e.close()
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-m", "wenet_b200.cli.fsk_demod", "--cu8", "4", "921416", "115177", "-", "-"],
+                         input=z["raw4"].tobytes(), stdout=subprocess.PIPE, env=env, check=True, timeout=300).stdout
+    assert out == z["bits4"].tobytes()
+
+
 def test_fine_timing_generic_path_vs_oracle(eng_mod, oracle_port, monkeypatch):
     """the fine-timing chain without the periodic-table shortcut (what wb_create selects when the host finds the
     reference's phi_ft recurrence not periodic) gives the same soft decisions and nin sequence"""

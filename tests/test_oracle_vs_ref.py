@@ -67,6 +67,18 @@ def test_fsk_4fsk(oracle_port, oracle_ref):
     assert np.array_equal(sa.view(np.uint32), sb.view(np.uint32)) and np.array_equal(la.view(np.uint32), lb.view(np.uint32))
 
 
+@pytest.mark.parametrize("M,fmt,ebno", [(4, "cu8", 4.0), (4, "cf32", 9.0), (2, "cs16", 3.0)])
+def test_fsk_hard_bits(oracle_port, oracle_ref, M, fmt, ebno):
+    """rx_bits of fsk_demod() (src/fsk.c:936-959), the output of `fsk_demod` without -s"""
+    if M == 4:
+        raw, _ = siggen.make_4fsk_stream(31, 3000, ebno_db=ebno, fmt=fmt)
+    else:
+        raw, _ = siggen.make_stream(32, n_packets=1, ebno_db=ebno, fmt=fmt, clock_ppm=2500.0)
+    a = oracle_port.fsk(921416, 115177, M=M).run_bits(raw, fmt)
+    b = oracle_ref.fsk(921416, 115177, M=M).run_bits(raw, fmt)
+    assert a.size > 3000 and np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("framing", ["v1", "v2"])
 def test_deframer_vs_cli(oracle_port, oracle_ref, framing):
     """deframer + sd_to_llr + decoder + CRC gate against the real drs232_ldpc / wenet_ldpc binaries, incl.

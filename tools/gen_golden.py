@@ -11,6 +11,8 @@ The outputs are committed; tests never read /root/reference.
   ldpc_llr.npz  soft-decision blocks -> reference sd_to_llr() LLRs -> run_ldpc_decoder() bits / iterations / parity
                 counts for max_iter 10 and 100
   phi0.npz      arguments around every breakpoint (+ specials) -> reference phi0()
+  fsk_hard.npz  hard-bit output (fsk_demod WITHOUT -s, one byte per bit): a noisy 4-FSK cu8 stream and a noisy v1 2-FSK
+                cs16 stream -> the reference CLI's bytes; `python tools/gen_golden.py hard` writes only this file
   tx.npz        transmit side: bit patterns -> the reference's fsk_mod_c samples (2-FSK at the v1
                 tones, 4-FSK); three payloads and their v1 / v2 on-air frame bits, accepted by the reference receiver
                 (this script checks that fsk_mod_c of those frames | fsk_demod | drs232_ldpc / wenet_ldpc returns
@@ -34,7 +36,25 @@ def cli(args, data):
     return subprocess.run(args, input=data, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
 
 
+def gen_hard():
+    fsk_demod = O.ref_cli("fsk_demod")
+    raw4, _ = siggen.make_4fsk_stream(21, 2400, ebno_db=5.0, fmt="cu8")
+    b4 = cli([fsk_demod, "--cu8", "4", "921416", "115177", "-", "-"], raw4.tobytes())
+    s4 = cli([fsk_demod, "--cu8", "-s", "4", "921416", "115177", "-", "-"], raw4.tobytes())
+    b4 = np.frombuffer(b4, np.uint8)
+    # the point of the vector: arg-max decisions are not the signs of the 4-FSK soft decisions
+    assert np.mean(b4 != (np.frombuffer(s4, np.float32) > 0)) > 0.01
+    raw2, _ = siggen.make_stream(22, n_packets=1, ebno_db=4.0, fmt="cs16", clock_ppm=-2000.0)
+    b2 = cli([fsk_demod, "--cs16", "2", "921416", "115177", "-", "-"], raw2.tobytes())
+    np.savez_compressed(os.path.join(GOLD, "fsk_hard.npz"), raw4=raw4, bits4=b4, raw2=raw2,
+                        bits2=np.frombuffer(b2, np.uint8))
+
+
 def main():
+    if sys.argv[1:] == ["hard"]:
+        gen_hard()
+        return
+    gen_hard()
     ref = O.Oracle("reference")
     fsk_demod, drs, wen = O.ref_cli("fsk_demod"), O.ref_cli("drs232_ldpc"), O.ref_cli("wenet_ldpc")
     os.makedirs(GOLD, exist_ok=True)

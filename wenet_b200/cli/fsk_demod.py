@@ -4,8 +4,9 @@
 Same argv, input formats, output stream and exit codes as reference src/fsk_demod.c:89-206, demodulating on the
 GPU through libwenet_b200.so.  Differences, all outside the hot path: -l (low-rate mode) and -f (test frames)
 are not implemented and exit 1; the stats JSON (stderr, -t) has the reference's keys (secs, EbNodB, ppm, f1_est,
-f2_est[, f3_est, f4_est], eye_diagram, samp_fft -- what rx/fskstatsudp.py parses) but is emitted per block of frames;
-without -s the hard bits are the signs of the soft decisions.  Output is written per block of frames, not per frame.
+f2_est[, f3_est, f4_est], eye_diagram, samp_fft -- what rx/fskstatsudp.py parses) but is emitted per block of frames.
+Without -s the output is the demodulator's own hard bits (arg-max tone, src/fsk.c:936-959), one byte per bit.
+Output is written per block of frames, not per frame.
 """
 import getopt
 import json
@@ -95,7 +96,7 @@ def main(argv=None):
     limits = (o["lo"], o["hi"]) if (o["lo"] > 0 and o["hi"] > o["lo"]) else None
     try:
         eng = E.Engine(1, Fs=o["Fs"], Rs=o["Rs"], M=o["M"], P=o["P"], in_fmt=o["fmt"], framing="none",
-                       chunk_samples=(BLOCK_FRAMES + 2) * 512, est_limits=limits, stats=o["stats"])
+                       chunk_samples=(BLOCK_FRAMES + 2) * 512, est_limits=limits, stats=o["stats"], hard_bits=not o["soft"])
     except E.WbError as e:
         sys.stderr.write("Couldn't open files\n%s\n" % e)
         sys.exit(1)
@@ -118,10 +119,8 @@ def main(argv=None):
         if sd.size:
             if o["soft"]:
                 fout.write(sd.tobytes())
-            elif o["M"] == 2:
-                fout.write((sd < 0).astype(np.uint8).tobytes())
             else:
-                fout.write((sd > 0).astype(np.uint8).tobytes())
+                fout.write(eng.drain_hard(0).tobytes())
             fout.flush()
         if o["stats"] and sd.size:
             frames_since += sd.size // eng.Nbits

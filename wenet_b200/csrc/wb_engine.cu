@@ -64,6 +64,8 @@ struct wb_engine {
     wb_stream_state *d_state;
     wb_cursor *d_cursor;
     float *d_sd;
+    unsigned char *d_hard;           /* WB_FLAG_HARD_BITS */
+    bool hard_valid;                 /* the last process call ran the demodulator */
     unsigned long long sd_stride;
     unsigned sd_cap;
     unsigned *d_jobs;
@@ -333,7 +335,7 @@ extern "C" void wb_destroy(wb_engine *e)
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    cudaFree(e->d_in); cudaFree(e->d_state); cudaFree(e->d_cursor); cudaFree(e->d_sd); cudaFree(e->d_jobs);
+    cudaFree(e->d_in); cudaFree(e->d_state); cudaFree(e->d_cursor); cudaFree(e->d_sd); cudaFree(e->d_hard); cudaFree(e->d_jobs);
     cudaFree(e->d_c4); cudaFree(e->d_cw); cudaFree(e->d_cw_packed); cudaFree(e->d_llr); cudaFree(e->d_llr_packed);
     cudaFree(e->d_gather); cudaFree(e->d_fill); cudaFree(e->d_frame_log); cudaFree(e->d_tables); cudaFree(e->d_vedge);
     cudaFree(e->d_crc_tab); cudaFree(e->d_scramble); cudaFree(e->d_lut);
@@ -371,12 +373,18 @@ static int init_states(wb_engine *e)
     return WB_OK;
 }
 
+template <int M, int TS, bool CF32, bool BLK, bool HARD>
+static cudaError_t fsk_set_attr3(size_t smem)
+{
+    cudaError_t ce = cudaFuncSetAttribute(wb_fsk_kernel<M, TS, CF32, BLK, HARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return ce;
+    return cudaFuncSetAttribute(wb_fsk_kernel<M, TS, CF32, BLK, HARD>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+}
 template <int M, int TS, bool CF32, bool BLK>
 static cudaError_t fsk_set_attr2(size_t smem)
 {
-    cudaError_t ce = cudaFuncSetAttribute(wb_fsk_kernel<M, TS, CF32, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ce != cudaSuccess) return ce;
-    return cudaFuncSetAttribute(wb_fsk_kernel<M, TS, CF32, BLK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaError_t ce = fsk_set_attr3<M, TS, CF32, BLK, false>(smem);
+    return ce != cudaSuccess ? ce : fsk_set_attr3<M, TS, CF32, BLK, true>(smem);
 }
 template <int M, int TS, bool CF32>
 static cudaError_t fsk_set_attr(size_t smem, bool blk)
@@ -405,7 +413,7 @@ extern "C" int wb_create(const wb_config *cfg, wb_engine **out)
     e->cfg = *cfg;
     e->stream = nullptr; e->tev0 = e->tev1 = nullptr;
     for (int i = 0; i < 8; i++) e->ev[i] = nullptr;
-    e->d_in = nullptr; e->d_state = nullptr; e->d_cursor = nullptr; e->d_sd = nullptr; e->d_jobs = nullptr; e->d_c4 = nullptr;
+    e->d_in = nullptr; e->d_state = nullptr; e->d_cursor = nullptr; e->d_sd = nullptr; e->d_hard = nullptr; e->hard_valid = false; e->d_jobs = nullptr; e->d_c4 = nullptr;
     e->d_cw = e->d_cw_packed = nullptr; e->d_llr = e->d_llr_packed = nullptr; e->d_gather = nullptr; e->d_fill = nullptr; e->d_frame_log = nullptr;
     e->d_tx_bits = nullptr; e->d_hrows = nullptr; e->tx_bits_stride = e->tx_nbits = 0;
     e->d_tables = nullptr; e->d_vedge = nullptr; e->d_crc_tab = nullptr; e->d_scramble = nullptr; e->d_lut = nullptr;
@@ -456,6 +464,10 @@ extern "C" int wb_create(const wb_config *cfg, wb_engine **out)
     CRE(cudaMalloc(&e->d_cursor, sizeof(wb_cursor) * n));
     CRE(cudaMalloc(&e->d_sd, sizeof(float) * e->sd_stride * n));
     CRE(cudaMemsetAsync(e->d_sd, 0, sizeof(float) * e->sd_stride * n, e->stream));
+    if (cfg->flags & WB_FLAG_HARD_BITS) {
+        CRE(cudaMalloc(&e->d_hard, (WB_HARD_PRE + (size_t)e->sd_cap) * n));
+        CRE(cudaMemsetAsync(e->d_hard, 0, (WB_HARD_PRE + (size_t)e->sd_cap) * n, e->stream));
+    }
     size_t nslots = (size_t)n * e->job_cap;
     CRE(cudaMalloc(&e->d_jobs, sizeof(unsigned) * nslots));
     CRE(cudaMalloc(&e->d_c4, sizeof(double) * nslots));
@@ -622,15 +634,22 @@ __global__ void wb_gather_kernel(const wb_codeword *cw, const float *llr, const 
     }
 }
 
-template <int M, int TS>
-static void launch_fsk(wb_engine *e, const wb_fsk_args &a)
+template <int M, int TS, bool HARD>
+static void launch_fsk2(wb_engine *e, const wb_fsk_args &a)
 {
     const int grid = (e->cfg.n_streams + e->spb - 1) / e->spb;
     const bool cf32 = e->fp.in_fmt == WB_FMT_CF32, blk = e->fp.step == 1;
-    if (cf32 && blk) wb_fsk_kernel<M, TS, true, true><<<grid, e->spb * 32, e->fsk_smem, e->stream>>>(e->fp, a);
-    else if (cf32) wb_fsk_kernel<M, TS, true, false><<<grid, e->spb * 32, e->fsk_smem, e->stream>>>(e->fp, a);
-    else if (blk) wb_fsk_kernel<M, TS, false, true><<<grid, e->spb * 32, e->fsk_smem, e->stream>>>(e->fp, a);
-    else wb_fsk_kernel<M, TS, false, false><<<grid, e->spb * 32, e->fsk_smem, e->stream>>>(e->fp, a);
+    if (cf32 && blk) wb_fsk_kernel<M, TS, true, true, HARD><<<grid, e->spb * 32, e->fsk_smem, e->stream>>>(e->fp, a);
+    else if (cf32) wb_fsk_kernel<M, TS, true, false, HARD><<<grid, e->spb * 32, e->fsk_smem, e->stream>>>(e->fp, a);
+    else if (blk) wb_fsk_kernel<M, TS, false, true, HARD><<<grid, e->spb * 32, e->fsk_smem, e->stream>>>(e->fp, a);
+    else wb_fsk_kernel<M, TS, false, false, HARD><<<grid, e->spb * 32, e->fsk_smem, e->stream>>>(e->fp, a);
+}
+/* WB_FLAG_HARD_BITS picks the instantiation that also writes rx_bits */
+template <int M, int TS>
+static void launch_fsk(wb_engine *e, const wb_fsk_args &a)
+{
+    if (a.hard) launch_fsk2<M, TS, true>(e, a);
+    else launch_fsk2<M, TS, false>(e, a);
 }
 
 /* K2 -> K3 -> K4 -> carry over whatever soft decisions the rows hold (cursor[s].n_sd of them per stream) */
@@ -682,13 +701,14 @@ extern "C" int wb_process(wb_engine *e)
     a.state = e->d_state; a.cursor = e->d_cursor; a.in = e->d_in; a.in_stride = e->in_stride;
     a.sd = e->d_sd; a.sd_stride = e->sd_stride; a.sd_cap = e->sd_cap; a.n_streams = n;
     a.compact = e->resident_mode ? 0 : 1; a.headroom = WB_HEADROOM; a.spb = e->spb;
-    a.frame_log = e->d_frame_log; a.log_cap = e->log_cap;
+    a.frame_log = e->d_frame_log; a.log_cap = e->log_cap; a.hard = e->d_hard;
     CU(cudaEventRecord(e->ev[0], e->stream));
     if (e->fp.M == 2 && e->fp.Ts == 8) launch_fsk<2, 8>(e, a);
     else if (e->fp.M == 2 && e->fp.Ts == 10) launch_fsk<2, 10>(e, a);
     else if (e->fp.M == 4 && e->fp.Ts == 8) launch_fsk<4, 8>(e, a);
     else launch_fsk<4, 10>(e, a);
     e->launches++;
+    e->hard_valid = true;
     CU(cudaEventRecord(e->ev[1], e->stream));
     int rc2 = launch_decode(e);
     if (rc2) return rc2;
@@ -732,6 +752,7 @@ extern "C" int wb_process_soft(wb_engine *e, const float *const *sd, const uint6
     CU(cudaMemcpyAsync(e->d_fill, cnt.data(), sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, e->stream));
     wb_set_nsd_kernel<<<(n + 127) / 128, 128, 0, e->stream>>>(e->d_cursor, e->d_fill, e->d_state, n);
     e->launches++;
+    e->hard_valid = false;
     CU(cudaEventRecord(e->ev[0], e->stream));
     CU(cudaEventRecord(e->ev[1], e->stream));
     rc = launch_decode(e);
@@ -849,6 +870,26 @@ extern "C" int wb_drain_soft(wb_engine *e, int stream, float *buf, size_t cap_fl
     if (n > cap_floats) return wb_fail(WB_ERANGE, "need %zu floats", n);
     if (n) {
         CU(cudaMemcpyAsync(buf, e->d_sd + (size_t)stream * e->sd_stride + WB_CARRY_CAP, sizeof(float) * n, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    return WB_OK;
+}
+
+extern "C" int wb_drain_hard(wb_engine *e, int stream, uint8_t *buf, size_t cap, size_t *nout)
+{
+    if (!e || !nout) return wb_fail(WB_EINVAL, "null argument");
+    if (stream < 0 || stream >= e->cfg.n_streams) return wb_fail(WB_EINVAL, "stream %d out of range", stream);
+    if (!e->d_hard) return wb_fail(WB_EINVAL, "hard bits need WB_FLAG_HARD_BITS");
+    if (!e->hard_valid) return wb_fail(WB_EINVAL, "no demodulator ran in the last process call");
+    int rc = wb_collect(e);
+    if (rc) return rc;
+    CU(cudaSetDevice(e->cfg.device));
+    size_t n = e->cursor[stream].n_sd;
+    *nout = n;
+    if (n > cap) return wb_fail(WB_ERANGE, "need %zu bytes", n);
+    if (n && !buf) return wb_fail(WB_EINVAL, "null buffer");
+    if (n) {
+        CU(cudaMemcpyAsync(buf, e->d_hard + (size_t)stream * (WB_HARD_PRE + (size_t)e->sd_cap) + WB_HARD_PRE, n, cudaMemcpyDeviceToHost, e->stream));
         CU(cudaStreamSynchronize(e->stream));
     }
     return WB_OK;

@@ -91,6 +91,7 @@ struct wb_fsk_args {
     unsigned headroom;             /* samples; wb_feed appends at this row offset after a compacting process */
     float *frame_log;              /* optional test tap [n_streams][log_cap][8] */
     int log_cap;
+    unsigned char *hard;           /* WB_FLAG_HARD_BITS: [n_streams][WB_HARD_PRE + sd_cap] one byte per bit (rx_bits of fsk_demod()), else NULL */
 };
 
 __device__ __forceinline__ float2 wb_cmul2(float2 a, float2 b)   /* reference src/comp_prim.h cmult */
@@ -300,7 +301,7 @@ __device__ unsigned long long wb_phase_clk[8];
 
 /* BLK: P == Ts (step 1), the configuration every Wenet script uses: the whole frame geometry is a compile-time
    constant (host and kernel share the wb_blk_* formulas of wb_internal.h).  !BLK: general P, geometry from p. */
-template <int M, int TS, bool CF32, bool BLK>
+template <int M, int TS, bool CF32, bool BLK, bool HARD>
 __global__ void __launch_bounds__(M == 2 ? 448 : 256, 2)
 wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 {
@@ -934,6 +935,36 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 for (int i = lane; i < NBITS; i += 32)
                     out[i] = (n_out >= (unsigned)NBITS) ? out[i - NBITS] : st->sd_last[i];
             }
+            if (HARD) {   /* a separate instantiation: the soft-only kernel keeps its register allocation */
+                /* rx_bits of fsk_demod(), reference src/fsk.c:936-959: the tone with the largest |t|^2 (first one
+                   wins a tie), NOT the sign of the soft decision (for 4-FSK the two disagree under noise) */
+                unsigned char *hb = a.hard + (size_t)sgw * (WB_HARD_PRE + (size_t)a.sd_cap) + WB_HARD_PRE + n_out;
+                if (!nan) {
+                    const float omf = __fsub_rn(1.0f, fract);
+                    for (int i = lane; i < NSYM; i += 32) {
+                        const int stt = (i + 1) * Pc;
+                        const int il = wb_phys<SWZ>(stt + low), ih = wb_phys<SWZ>(stt + high);
+                        float mx = 0.0f;
+                        int sym = 0;
+#pragma unroll
+                        for (int m = 0; m < M; m++) {
+                            const float2 *fi = (m == 0) ? X + xo : Y + (m - 1) * ylen;
+                            const float2 lo = fi[il], hi = fi[ih];
+                            const float tr = __fadd_rn(__fmul_rn(omf, lo.x), __fmul_rn(fract, hi.x));
+                            const float ti = __fadd_rn(__fmul_rn(omf, lo.y), __fmul_rn(fract, hi.y));
+                            const float t2 = __fadd_rn(__fmul_rn(tr, tr), __fmul_rn(ti, ti));
+                            if (m == 0) mx = t2;
+                            else if (t2 > mx) { mx = t2; sym = m; }
+                        }
+                        if (M == 2) hb[i] = (unsigned char)(sym == 1);
+                        else { hb[2 * i + 1] = (unsigned char)(sym & 1); hb[2 * i] = (unsigned char)((sym & 2) >> 1); }
+                    }
+                } else {
+                    /* NaN guard: the caller's bit buffer keeps the previous frame's bits (for the first frame of a
+                       chunk they sit right before it in the row, where the previous launch left them) */
+                    for (int i = lane; i < NBITS; i += 32) hb[i] = hb[i - NBITS];
+                }
+            }
             if (p.stats && !nan) {
                 /* Eb/N0 terms, reference src/fsk.c:985-1010: meanebno / stdebno accumulate over the symbols in order
                    (every lane repeats the 48-step sum from shuffled-in values), the log10 is left to the host */
@@ -1030,6 +1061,10 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
         if (n_out >= (unsigned)NBITS) {
             const float *lastf = WB_ROW_SD(sg) + n_out - NBITS;
             for (int i = lane; i < NBITS; i += 32) st->sd_last[i] = lastf[i];
+            if (HARD) {
+                unsigned char *hrow = a.hard + (size_t)sg * (WB_HARD_PRE + (size_t)a.sd_cap) + WB_HARD_PRE;
+                for (int i = lane; i < NBITS; i += 32) hrow[i - NBITS] = hrow[n_out - NBITS + i];
+            }
         }
         const unsigned char *in = WB_ROW_IN(sg);
         const unsigned long long rem = fill - pos;

@@ -6,6 +6,8 @@
  *   d_state   [n_streams]             wb_stream_state (persistent modem + deframer state)
  *   d_sd      [n_streams][sd_stride]  float soft decisions: [carry of a half-collected packet | this chunk]
  *                                     the chunk starts at float index WB_CARRY_CAP of the row
+ *   d_hard    [n_streams][WB_HARD_PRE + sd_cap]  uint8 hard bits, only with WB_FLAG_HARD_BITS: [.. last frame of the
+ *                                     previous chunk | this chunk], the chunk starts at byte WB_HARD_PRE of the row
  *   d_cursor  [n_streams]             wb_cursor (what the host reads back after every wb_process)
  *   d_jobs    [n_streams][job_cap]    unsigned: row offset of the first collected symbol of each codeword
  *   d_c4      [n_streams][job_cap]    double: 4 * estEsN0 of each codeword (sd_to_llr statistics)
@@ -32,6 +34,7 @@
 #define WB_FRAME_SYMS 48               /* nsyms, reference src/fsk.c:134 */
 
 #define WB_PKT_BODY_BYTES 323          /* 256 payload + 2 crc + 65 parity */
+#define WB_HARD_PRE 128                /* >= 2 * WB_FRAME_SYMS: room for the previous chunk's last frame of hard bits */
 #define WB_CARRY_CAP 3264              /* >= 3230 symbols of a half-collected v1 packet, 64-float aligned */
 
 #define WB_LDPC_THREADS 288            /* 9 warps: 516 checks = 2 rounds, 2580 variables = 9 rounds */

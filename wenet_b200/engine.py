@@ -25,6 +25,7 @@ FMT_BPS = {"cf32": 8, "cu8": 2, "cs16": 4, "s16": 2}
 FRAMING = {"none": 0, None: 0, "v1": 1, "v2": 2}
 FLAG_KEEP_LLR = 1
 FLAG_STATS = 2
+FLAG_HARD_BITS = 4
 
 WB_OK, WB_EINVAL, WB_ENOMEM, WB_ECUDA, WB_ENODEV, WB_ERANGE = 0, -1, -2, -3, -4, -5
 NCODE = 2580
@@ -78,6 +79,7 @@ ABI = [
     ("wb_drain_packets", C.c_int, [_VP, C.c_int, _VP, _SZ, C.POINTER(_SZ)]),
     ("wb_drain_all_packets", C.c_int, [_VP, _VP, _SZ, C.POINTER(_SZ), C.POINTER(_U64)]),
     ("wb_drain_soft", C.c_int, [_VP, C.c_int, _VP, _SZ, C.POINTER(_SZ)]),
+    ("wb_drain_hard", C.c_int, [_VP, C.c_int, _VP, _SZ, C.POINTER(_SZ)]),
     ("wb_drain_codewords", C.c_int, [_VP, _VP, _VP, _SZ, C.POINTER(_SZ)]),
     ("wb_get_stats", C.c_int, [_VP, C.c_int, C.POINTER(WbStats)]),
     ("wb_clear_estimators", C.c_int, [_VP]),
@@ -157,7 +159,7 @@ class Engine:
     """
 
     def __init__(self, n_streams, Fs=921416, Rs=115177, M=2, P=0, in_fmt="cf32", framing="v1", max_iter=0,
-                 chunk_samples=1 << 20, device=0, est_limits=None, keep_llr=False, stats=False):
+                 chunk_samples=1 << 20, device=0, est_limits=None, keep_llr=False, stats=False, hard_bits=False):
         self.lib = load_library()
         self.fmt = in_fmt
         cfg = WbConfig()
@@ -169,7 +171,8 @@ class Engine:
         cfg.in_fmt = FMT[in_fmt]
         cfg.framing = FRAMING[framing]
         cfg.ldpc_max_iter = max_iter
-        cfg.flags = (FLAG_KEEP_LLR if keep_llr else 0) | (FLAG_STATS if stats else 0)
+        cfg.flags = ((FLAG_KEEP_LLR if keep_llr else 0) | (FLAG_STATS if stats else 0)
+                     | (FLAG_HARD_BITS if hard_bits else 0))
         cfg.chunk_samples = chunk_samples
         self.h = _VP()
         self._check(self.lib.wb_create(C.byref(cfg), C.byref(self.h)))
@@ -281,6 +284,14 @@ class Engine:
         buf = np.empty(self.sd_cap, dtype=np.float32)
         n = C.c_size_t(0)
         self._check(self.lib.wb_drain_soft(self.h, stream, _ptr(buf), buf.size, C.byref(n)))
+        return buf[:n.value].copy()
+
+    def drain_hard(self, stream):
+        """Hard bits (one byte each) `stream` produced in the last process(): what fsk_demod without -s writes,
+        the rx_bits of fsk_demod() (reference src/fsk.c:936-959).  Needs hard_bits=True."""
+        buf = np.empty(self.sd_cap, dtype=np.uint8)
+        n = C.c_size_t(0)
+        self._check(self.lib.wb_drain_hard(self.h, stream, _ptr(buf), buf.size, C.byref(n)))
         return buf[:n.value].copy()
 
     def drain_codewords(self, with_llr=False):
