@@ -497,6 +497,15 @@ extern "C" int wb_create(const wb_config *cfg, wb_engine **out)
             for (int t = max_spb; t >= (ctas == 2 ? 4 : 2); t--)      /* >= 2: the re and im fine-timing chains run in warps 0 and 1 */
                 if (smem_for(t) <= (size_t)dev_smem_blk && ctas * (smem_for(t) + 1024) <= (size_t)dev_smem_sm) { spb = t; break; }
         if (spb == 0) { wb_destroy(e); return wb_fail(WB_EINVAL, "FSK kernel does not fit shared memory"); }
+        /* fewer streams than one full CTA per SM: spread them, one smaller CTA on every SM instead of full CTAs on some
+           of them (1024 streams on a B200: 74 CTAs x 14 streams 34.8 ms per 1 Mi-sample chunk, 147 x 7 28.2 ms; 512
+           streams: 37 x 14 34.7 ms, 128 x 4 26.7 ms; from one CTA per SM up the full CTA wins: 2048 streams 35.1 vs
+           36.9 ms; tools/sweep_spb.sh) */
+        {
+            int n_sm = 0;
+            CRE(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+            if (n_sm > 0 && (n + spb - 1) / spb < n_sm) spb = std::min(spb, std::max(4, (n + n_sm - 1) / n_sm));
+        }
         if (getenv("WB_FSK_SPB")) spb = std::max(2, std::min(max_spb, atoi(getenv("WB_FSK_SPB"))));
         e->spb = spb;
         /* segments of the sequential mixer phase (see wb_fsk_kernel.cuh, B1): multiples of 8 steps, shrinking
