@@ -99,6 +99,7 @@ STREAM_CASES = [
     ("cs16_9dB_negppm", "cs16", 9.0, -3000.0, 2),
     ("cu8_12dB", "cu8", 12.0, 0.0, 2),
     ("cf32_5dB", "cf32", 5.0, 0.0, 2),
+    ("s16_real_14dB_ppm", "s16", 14.0, 1500.0, 2),      # fsk_demod without -c/-d: real samples, imag = 0 (src/fsk_demod.c:289-295)
 ]
 
 

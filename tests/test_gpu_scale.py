@@ -122,7 +122,7 @@ def test_config5_4fsk_1024_streams(E, oracle_port):
 
 def test_edge_cases(E, oracle_port):
     """empty feeds, sub-frame dribbles, NaN samples (the reference's NaN guard, src/fsk.c:878-880), saturated input"""
-    e = E.Engine(3, in_fmt="cf32", framing="v1", chunk_samples=8192)
+    e = E.Engine(3, in_fmt="cf32", framing="v1", chunk_samples=8192, hard_bits=True)
     e.feed([None, None, None]); e.process(); e.sync()
     assert e.last_samples == 0 and all(e.drain_soft(s).size == 0 for s in range(3))
     raw, _ = siggen.make_stream(5, n_samples=6000, ebno_db=10.0, fmt="cf32")
@@ -131,7 +131,8 @@ def test_edge_cases(E, oracle_port):
     bad[2 * 1000] = np.nan                                   # one NaN sample in frame 2
     sat = np.clip(raw * 1e30, -3e38, 3e38).astype(np.float32)
     ref = [oracle_port.fsk(921416, 115177).run(x, "cf32")[0] for x in (raw, bad, sat)]
-    got = [[], [], []]
+    ref_bits = [oracle_port.fsk(921416, 115177).run_bits(x, "cf32") for x in (raw, bad, sat)]
+    got, got_bits = [[], [], []], [[], [], []]
     pos = 0
     while pos < raw.size:                                    # 101-sample dribbles: most calls complete no frame
         n = 202
@@ -139,11 +140,14 @@ def test_edge_cases(E, oracle_port):
         e.process(); e.sync()
         for s in range(3):
             got[s].append(e.drain_soft(s))
+            got_bits[s].append(e.drain_hard(s))
         pos += n
     for s in range(3):
         g = np.concatenate(got[s])
         assert g.size == ref[s].size, s
         same = (g.view(np.uint32) == ref[s].view(np.uint32)) | (np.isnan(g) & np.isnan(ref[s]))
         assert same.all(), (s, np.nonzero(~same)[0][:5])
+        # hard bits: a frame the NaN guard skips repeats the previous frame's bits (the caller's buffer is left as it was)
+        assert np.array_equal(np.concatenate(got_bits[s]), ref_bits[s]), s
     assert set(e.nin().tolist()) <= {380, 384, 388}
     e.close()

@@ -41,7 +41,8 @@ def test_ldpc_decode(oracle_port, oracle_ref, max_iter):
 
 FSK_CASES = [("cf32", 2, None, siggen.V1, 9.0, 0.0), ("cs16", 2, None, siggen.V1, 7.0, 3000.0),
              ("cu8", 2, None, siggen.V1, 12.0, -2500.0), ("cf32", 2, None, siggen.V2, 9.0, 1500.0),
-             ("cf32", 2, 4, siggen.V1, 10.0, 0.0), ("cs16", 2, 5, siggen.V2, 10.0, 0.0)]
+             ("cf32", 2, 4, siggen.V1, 10.0, 0.0), ("cs16", 2, 5, siggen.V2, 10.0, 0.0),
+             ("s16", 2, None, siggen.V1, 14.0, 1500.0)]
 
 
 @pytest.mark.parametrize("fmt,M,P,cfg,ebno,ppm", FSK_CASES)
