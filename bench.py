@@ -429,13 +429,16 @@ def main():
     fsk_gbs = alg_bps * samples_step / (kms[0] * 1e-3) / 1e9 if kms[0] > 0 else 0.0
     # DRAM traffic of the dominant kernel per launch: one `ncu --set full` capture of this same workload
     # (profiles/r01_traffic.json says how it was taken); null for any other workload
-    traffic = None
+    traffic = issue_pct = None
     try:
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
             tj = json.load(fh)
         w = tj["wb_fsk_kernel"]["workload"]
         if w["streams"] == n and w["chunk_samples"] == chunk and w["in_fmt"] == "cf32" and args.mode == "v1":
             traffic = tj["wb_fsk_kernel"]["dram_bytes_read"] + tj["wb_fsk_kernel"]["dram_bytes_write"]
+            # what actually bounds the kernel (SURVEY 8d asks for it beside the HBM fraction): issue-slot utilisation
+            # from the same ncu capture, smsp__issue_active.avg.pct_of_peak_sustained_active
+            issue_pct = tj["wb_fsk_kernel"].get("issue_active_pct")
     except Exception:
         traffic = None
     roofline = {"bound": "hbm", "kernel": "wb_fsk_kernel", "achieved": round(fsk_gbs, 2), "peak": peak, "unit": "GB/s",
@@ -443,7 +446,10 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "kernel_ms": {"fsk": round(float(kms[0]), 3), "deframe": round(float(kms[1]), 3),
                               "llr_stats": round(float(kms[2]), 3), "ldpc": round(float(kms[3]), 3)},
-                "alg_bytes_per_launch": alg_bps * samples_step}
+                "alg_bytes_per_launch": alg_bps * samples_step,
+                "issue_active_pct": issue_pct,
+                "note": "the kernel is a chain of dependent fp32 phases per frame (bit-exact with the reference's operation "
+                        "order): issue slots, not HBM, are the binding resource; see DESIGN.md section 4"}
 
     # ---- e2e through the public API with host buffers ----
     def run_e2e(fmt, n_eng):
