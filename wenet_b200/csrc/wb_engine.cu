@@ -849,6 +849,7 @@ extern "C" int wb_drain_all_packets(wb_engine *e, uint8_t *buf, size_t cap, size
     size_t need = 0;
     for (auto &q : e->packets) need += q.size() / WB_PACKET_BYTES * rec;
     if (need > cap) { *nbytes = need; return wb_fail(WB_ERANGE, "need %zu bytes", need); }
+    if (need && !buf) return wb_fail(WB_EINVAL, "null buffer");
     size_t o = 0; uint64_t np = 0;
     for (int s = 0; s < e->cfg.n_streams; s++) {
         wb_engine::pktq &q = e->packets[s];
