@@ -82,6 +82,21 @@ def test_fsk_hard_bits(oracle_port):
     assert np.array_equal(b2, z["bits2"])
 
 
+def test_testframe_counter():
+    """`fsk_demod -f` bookkeeping (src/fsk_demod.c:226-243, :304-343; host side, wenet_b200/cli/_testframes.py) on the
+    reference CLI's own hard bits: the same "errs: ..." lines, whatever the block size the bits arrive in"""
+    from wenet_b200.cli._testframes import TestFrames
+    z = g("testframes.npz")
+    want = z["stderr"].tobytes().decode()
+    assert want.count("errs:") == 40
+    for block in (48, 48 * 7, 48 * 64, 10 ** 6):
+        tf, got = TestFrames(), []
+        for k in range(0, z["bits"].size, block):
+            got += [tf.line(h) for h in tf.feed(z["bits"][k:k + block])]
+        assert "".join(got) == want, block
+        assert (tf.frames, tf.bits) == (40, 4000)
+
+
 def test_tx_side(oracle_port):
     """transmit side: the modulator restatement against the reference's fsk_mod_c output, the frame
     builder against frames the reference receiver accepted, the scramble table against tx/radio_wrappers.py's"""

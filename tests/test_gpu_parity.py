@@ -282,6 +282,51 @@ def test_hard_bits_golden_and_cli(eng_mod):
     assert out == z["bits4"].tobytes()
 
 
+def test_cli_start_rx_command_line():
+    """the stage-1 command of start_rx.sh:126 as it is written there (--stats=100: an option with an optional argument):
+    the reference's soft decisions on stdout, JSON lines with the keys rx/fskstatsudp.py:214-226 reads on stderr"""
+    import json
+    import subprocess
+    import sys
+    z = np.load(os.path.join(GOLD, "fsk_v1.npz"))
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-m", "wenet_b200.cli.fsk_demod", "--cu8", "-s", "--stats=100", "2", "921416", "115177",
+                        "-", "-"], input=z["raw"].tobytes(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env,
+                       check=True, timeout=300)
+    assert r.stdout == z["sd"].tobytes()
+    recs = [json.loads(l) for l in r.stderr.decode().splitlines() if l.startswith("{")]
+    assert recs
+    for k in ("EbNodB", "ppm", "f1_est", "f2_est", "samp_fft", "eye_diagram"):
+        assert k in recs[-1], k
+    # the reference's own estimates at the end of this stream (oracle/_ref, estimator bins 39 and 76 of 3599.28 Hz)
+    assert len(recs[-1]["samp_fft"]) == 128
+    assert abs(recs[-1]["f1_est"] - 140372.0) < 1 and abs(recs[-1]["f2_est"] - 273545.4) < 1
+
+
+def test_cli_testframe_mode():
+    """`fsk_demod -f` through the stand-in: the reference CLI's hard bits on stdout and its "errs: ..." lines on stderr
+    (tests/golden/testframes.npz, written by the reference binary), hard and soft output modes"""
+    import subprocess
+    import sys
+    z = np.load(os.path.join(GOLD, "testframes.npz"))
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    cmd = [sys.executable, "-m", "wenet_b200.cli.fsk_demod", "--cs16", "-f"]
+    r = subprocess.run(cmd + ["2", "921416", "115177", "-", "-"], input=z["raw"].tobytes(), stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, env=env, check=True, timeout=300)
+    assert r.stdout == z["bits"].tobytes()
+    assert r.stderr.decode() == z["stderr"].tobytes().decode()
+    r = subprocess.run(cmd + ["-s", "2", "921416", "115177", "-", "-"], input=z["raw"].tobytes(), stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, env=env, check=True, timeout=300)
+    assert r.stderr.decode().count("errs:") == 40 and "bits tested 4000" in r.stderr.decode()
+    r = subprocess.run(cmd + ["-t", "2", "921416", "115177", "-", "-"], input=z["raw"].tobytes(), stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, env=env, check=True, timeout=300)
+    import json
+    recs = [json.loads(l) for l in r.stderr.decode().splitlines()]
+    assert recs and recs[-1]["frames"] == 40 and recs[-1]["bits"] == 4000 and recs[-1]["errs"] == 184
+    assert "eye_diagram" not in recs[-1]
+    assert abs(recs[-1]["f1_est"] - 140372.0) < 1 and abs(recs[-1]["f2_est"] - 273545.4) < 1   # the reference's values
+
+
 def test_fine_timing_generic_path_vs_oracle(eng_mod, oracle_port, monkeypatch):
     """the fine-timing chain without the periodic-table shortcut (what wb_create selects when the host finds the
     reference's phi_ft recurrence not periodic) gives the same soft decisions and nin sequence"""

@@ -13,6 +13,8 @@ The outputs are committed; tests never read /root/reference.
   phi0.npz      arguments around every breakpoint (+ specials) -> reference phi0()
   fsk_hard.npz  hard-bit output (fsk_demod WITHOUT -s, one byte per bit): a noisy 4-FSK cu8 stream and a noisy v1 2-FSK
                 cs16 stream -> the reference CLI's bytes; `python tools/gen_golden.py hard` writes only this file
+  testframes.npz  `fsk_demod -f`: the reference's known 100-bit frame sent 40 times at 7 dB -> the reference CLI's hard
+                bits (stdout) and its "errs: ..." lines (stderr); `python tools/gen_golden.py hard` writes this file too
   tx.npz        transmit side: bit patterns -> the reference's fsk_mod_c samples (2-FSK at the v1
                 tones, 4-FSK); three payloads and their v1 / v2 on-air frame bits, accepted by the reference receiver
                 (this script checks that fsk_mod_c of those frames | fsk_demod | drs232_ldpc / wenet_ldpc returns
@@ -48,6 +50,24 @@ def gen_hard():
     b2 = cli([fsk_demod, "--cs16", "2", "921416", "115177", "-", "-"], raw2.tobytes())
     np.savez_compressed(os.path.join(GOLD, "fsk_hard.npz"), raw4=raw4, bits4=b4, raw2=raw2,
                         bits2=np.frombuffer(b2, np.uint8))
+    raw = testframe_signal()
+    r = subprocess.run([fsk_demod, "--cs16", "-f", "2", "921416", "115177", "-", "-"], input=raw.tobytes(),
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+    assert r.stderr.count(b"errs:") >= 30
+    np.savez_compressed(os.path.join(GOLD, "testframes.npz"), raw=raw, bits=np.frombuffer(r.stdout, np.uint8),
+                        stderr=np.frombuffer(r.stderr, np.uint8))
+
+
+def testframe_signal(n_frames=40, ebno_db=7.0, seed=5):
+    """the known frame of src/fsk_demod.c:236-240 back to back through the oracle's restatement of fsk_mod_c, AWGN, cs16"""
+    from wenet_b200.cli._testframes import tx_frame
+    port = O.Oracle("port")
+    bits = np.concatenate([np.ones(960, np.uint8), np.tile(tx_frame(), n_frames), np.ones(480, np.uint8)])
+    bits = np.concatenate([bits, np.ones((-bits.size) % 48, np.uint8)])
+    x = port.fsk_mod(bits, 921416, 115177, 129763, 143594, M=2).astype(np.float64) / 2.0
+    x = x[0::2] + 1j * x[1::2]
+    y = siggen.add_noise(x, ebno_db, 921416, 115177, np.random.default_rng(seed))
+    return siggen.to_format(y / np.max(np.abs(y)), "cs16")
 
 
 def main():

@@ -2,9 +2,12 @@
 """fsk_demod [-l] [-p P] [-s] [(-c|-d)] [-t[r]] [-f] [-b lo] [-u hi] (2|4) SampleRate SymbolRate In Out
 
 Same argv, input formats, output stream and exit codes as reference src/fsk_demod.c:89-206, demodulating on the
-GPU through libwenet_b200.so.  Differences, all outside the hot path: -l (low-rate mode) and -f (test frames)
-are not implemented and exit 1; the stats JSON (stderr, -t) has the reference's keys (secs, EbNodB, ppm, f1_est,
-f2_est[, f3_est, f4_est], eye_diagram, samp_fft -- what rx/fskstatsudp.py parses) but is emitted per block of frames.
+GPU through libwenet_b200.so.  Differences, all outside the hot path: -l (low-rate mode: another frame geometry,
+used by no Wenet script) is not implemented and exits 1; the stats JSON (stderr, -t) has the reference's keys (secs,
+EbNodB, ppm, f1_est, f2_est[, f3_est, f4_est], eye_diagram, samp_fft -- what rx/fskstatsudp.py parses) but is emitted
+per block of frames.  -f (testframe mode, src/fsk_demod.c:226-243, :304-343) counts bit errors against the reference's
+known frame on the host (wenet_b200/cli/_testframes.py): the same "errs: ..." lines, or with -t one JSON line per modem
+frame that completed a testframe (modem statistics in it are the block's, the frames/bits/errs counters exact).
 Without -s the output is the demodulator's own hard bits (arg-max tone, src/fsk.c:936-959), one byte per bit.
 Output is written per block of frames, not per frame.
 """
@@ -35,21 +38,55 @@ def usage(prog, msg=None):
     sys.exit(1)
 
 
+def _split_stats_option(args):
+    """-t[r] / --stats[=r] takes an OPTIONAL argument (getopt_long "t::", src/fsk_demod.c:92-110), which Python's getopt
+    does not know: the value only counts when attached (`-t100`, `--stats=100`, the form every start_rx script uses),
+    a bare `-t` / `--stats` never swallows the next word.  Returns (remaining args, enabled, rate string or None)."""
+    rest, enabled, rate = [], False, None
+    takes_value = False                       # the previous word was -p / -b / -u: this one is its value
+    for a in args:
+        if takes_value or a == "--" or not a.startswith("-") or a == "-":
+            takes_value = False
+            rest.append(a)
+            continue
+        if a == "--stats" or a.startswith("--stats="):
+            enabled, rate = True, (a[8:] if a.startswith("--stats=") else None)
+            continue
+        if not a.startswith("--"):
+            k = 1
+            while k < len(a) and a[k] in "fhlcds":      # flags without an argument may be clustered in front
+                k += 1
+            if k < len(a) and a[k] == "t":
+                enabled, rate = True, (a[k + 1:] or None)
+                if k > 1:
+                    rest.append(a[:k])
+                continue
+            takes_value = a[-1] in "pbu" and all(c in "fhlcds" for c in a[1:-1])
+        rest.append(a)
+    return rest, enabled, rate
+
+
 def parse(argv):
+    rest, stats_on, stats_rate = _split_stats_option(argv[1:])
     try:
-        opts, args = getopt.gnu_getopt(argv[1:], "fhlp:cdt::sb:u:",
-                                       ["help", "lbr", "conv=", "cs16", "cu8", "fsk_lower=", "fsk_upper=", "stats=",
-                                        "stats", "soft-dec", "testframes"])
+        opts, args = getopt.gnu_getopt(rest, "fhlp:cdsb:u:",
+                                       ["help", "lbr", "conv=", "cs16", "cu8", "fsk_lower=", "fsk_upper=", "soft-dec",
+                                        "testframes"])
     except getopt.GetoptError as e:
         usage(argv[0], str(e))
-    o = dict(fmt="s16", soft=False, stats=False, stats_rate=8, P=0, lo=0, hi=0)
+    o = dict(fmt="s16", soft=False, stats=stats_on, stats_rate=8, P=0, lo=0, hi=0, testframes=False)
+    if stats_rate:
+        try:
+            o["stats_rate"] = int(stats_rate) or 8        # atoi() == 0 -> 8, src/fsk_demod.c:126-129
+        except ValueError:
+            o["stats_rate"] = 8
     for k, v in opts:
         if k in ("-h", "--help"):
             usage(argv[0])
         elif k in ("-l", "--lbr"):
             usage(argv[0], "low-rate mode (-l) is not supported by the B200 engine")
         elif k in ("-f", "--testframes"):
-            usage(argv[0], "testframe mode (-f) is not supported by the B200 engine")
+            o["testframes"] = True
         elif k in ("-c", "--cs16"):
             o["fmt"] = "cs16"
         elif k in ("-d", "--cu8"):
@@ -62,13 +99,6 @@ def parse(argv):
             o["lo"] = int(v or 0)
         elif k in ("-u", "--fsk_upper"):
             o["hi"] = int(v or 0)
-        elif k in ("-t", "--stats"):
-            o["stats"] = True
-            if v:
-                try:
-                    o["stats_rate"] = int(v) or 8
-                except ValueError:
-                    o["stats_rate"] = 8
     if len(args) < 5:
         usage(argv[0], "Too few arguments")
     if len(args) > 5:
@@ -107,6 +137,10 @@ def main(argv=None):
     dt = E.FMT_DTYPE[o["fmt"]]
     stats_every = int(1 / (o["stats_rate"] * eng.N / o["Fs"])) + 1 if o["stats"] else 0
     frames_since = 0
+    tf = None
+    if o["testframes"]:
+        from wenet_b200.cli._testframes import TestFrames
+        tf = TestFrames()
     while True:
         raw = fin.read(BLOCK_FRAMES * eng.N * bps)
         if not raw:
@@ -122,6 +156,24 @@ def main(argv=None):
             else:
                 fout.write(eng.drain_hard(0).tobytes())
             fout.flush()
+        if tf is not None and sd.size:
+            # src/fsk_demod.c:304-343: soft mode slices sd < 0 (whatever M is), hard mode takes the demodulator's bits
+            hits = tf.feed((sd < 0).astype(np.uint8) if o["soft"] else eng.drain_hard(0))
+            if not o["stats"]:
+                for h in hits:
+                    sys.stderr.write(tf.line(h))
+            elif hits:
+                st = eng.stats(0)
+                last = {}
+                for h in hits:                      # one line per modem frame that saw a testframe, counters as at its end
+                    last[h[0] // eng.Nbits] = h
+                for h in last.values():
+                    d = '{"secs": %d, "EbNodB": %5.1f, "ppm": %4d, "f1_est":%.1f, "f2_est":%.1f' % (
+                        int(time.time()), st.EbNodB, int(st.ppm), st.f_est[0], st.f_est[1])
+                    if o["M"] == 4:
+                        d += ', "f3_est":%.1f, "f4_est":%.1f' % (st.f_est[2], st.f_est[3])
+                    sys.stderr.write(d + ', "frames":%d, "bits":%d, "errs":%d}\n' % (h[2], h[3], h[4]))
+            continue
         if o["stats"] and sd.size:
             frames_since += sd.size // eng.Nbits
             if frames_since >= stats_every:
