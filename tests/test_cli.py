@@ -49,3 +49,10 @@ def test_ldpc_usage_errors():
         assert r.returncode == 1 and b"usage:" in r.stderr
         r = run(mod, "/nonexistent/in", "-")
         assert r.returncode == 1 and b"Error opening input file" in r.stderr
+
+
+def test_per_formatting_matches_the_reference_printf():
+    """(float)packet_errors/packets through %4.3f (src/drs232_ldpc.c:261-265, :280); with no packets at all the
+    reference binary prints -nan (checked against oracle/_ref/drs232_ldpc on empty input)"""
+    from wenet_b200.cli._ldpc_cli import _per
+    assert (_per(0, 0), _per(0, 2), _per(1, 3), _per(2, 3), _per(5, 5)) == ("-nan", "0.000", "0.333", "0.667", "1.000")

@@ -6,6 +6,13 @@ import numpy as np
 BLOCK_SYMS = 1 << 15
 
 
+def _per(errors, packets):
+    """(float)packet_errors/packets through %4.3f: 0/0 is the x86 default NaN, which glibc prints as -nan"""
+    if packets == 0:
+        return "-nan" if errors == 0 else "inf"
+    return "%4.3f" % float(np.float32(errors) / np.float32(packets))
+
+
 def main(argv, framing, name):
     if len(argv) < 3:
         sys.stderr.write("usage: %s InputOneSymbolPerFloat OutputPackets [-v[v]]\n" % name)
@@ -40,14 +47,12 @@ def main(argv, framing, name):
             if not cw["crc_ok"]:
                 errors = (errors + 1) & 0xFFFF
             if verbose:
-                sys.stderr.write("packets: %d packet_errors: %d PER: %4.3f iter: %d\n"
-                                 % (packets, errors, errors / packets if packets else float("nan"), cw["iters"]))
+                sys.stderr.write("packets: %d packet_errors: %d PER: %s iter: %d\n" % (packets, errors, _per(errors, packets), cw["iters"]))
         pk = eng.drain_packets(0)
         if pk:
             fout.write(pk)
             fout.flush()
     fout.flush()
-    sys.stderr.write("packets: %d packet_errors: %d PER: %4.3f\n"
-                     % (packets, errors, errors / packets if packets else float("nan")))
+    sys.stderr.write("packets: %d packet_errors: %d PER: %s\n" % (packets, errors, _per(errors, packets)))
     eng.close()
     return 0
