@@ -215,6 +215,15 @@ class Engine:
             raise TypeError("stream data must be %s for in_fmt=%s" % (FMT_DTYPE[self.fmt], self.fmt))
         return a
 
+    def _hold(self, arrays):
+        """Host arrays handed to an asynchronous copy stay referenced until the copies have run: until sync(), or until
+        the first feed after a process() -- wb_feed / wb_process_soft wait for a pending wb_process (and with it for every
+        copy queued before it) before they queue anything new.  Several feeds may be queued before one process()."""
+        if getattr(self, "_keep", None) is None or getattr(self, "_processed", False):
+            self._keep = []
+        self._processed = False
+        self._keep.extend(arrays)
+
     def feed(self, streams):
         """Append samples: ``streams[s]`` is the raw array of stream s (None/empty to skip)."""
         assert len(streams) == self.n_streams
@@ -227,8 +236,7 @@ class Engine:
             ptrs[s] = a.ctypes.data
             ns[s] = a.size // FMT_ELEMS[self.fmt]
         self._check(self.lib.wb_feed(self.h, ptrs, _ptr(ns)))
-        self._check(self.lib.wb_sync(self.h)) if False else None
-        self._keep = keep           # keep the host arrays alive until the copies have run
+        self._hold(keep)            # keep the host arrays alive until the copies have run
 
     def feed_strided(self, block):
         """Append the same number of samples to every stream from one [n_streams, elems] array."""
@@ -237,10 +245,11 @@ class Engine:
         assert block.strides[-1] == block.itemsize
         nsamp = block.shape[1] // FMT_ELEMS[self.fmt]
         self._check(self.lib.wb_feed_strided(self.h, C.c_void_p(block.ctypes.data), block.strides[0], nsamp))
-        self._keep = [block]
+        self._hold([block])
 
     def process(self):
         self._check(self.lib.wb_process(self.h))
+        self._processed = True
 
     def process_soft(self, streams):
         """Deframe + decode float32 soft symbols directly (what `drs232_ldpc` / `wenet_ldpc` read on stdin)."""
@@ -254,7 +263,8 @@ class Engine:
             ptrs[s] = a.ctypes.data
             ns[s] = a.size
         self._check(self.lib.wb_process_soft(self.h, ptrs, _ptr(ns)))
-        self._keep = keep
+        self._hold(keep)
+        self._processed = True
 
     def sync(self):
         self._check(self.lib.wb_sync(self.h))
