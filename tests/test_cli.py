@@ -56,3 +56,133 @@ def test_per_formatting_matches_the_reference_printf():
     reference binary prints -nan (checked against oracle/_ref/drs232_ldpc on empty input)"""
     from wenet_b200.cli._ldpc_cli import _per
     assert (_per(0, 0), _per(0, 2), _per(1, 3), _per(2, 3), _per(5, 5)) == ("-nan", "0.000", "0.333", "0.667", "1.000")
+
+
+class _FakeStats:
+    EbNodB, ppm, rx_timing = 9.5, 12.0, 0.1
+    f_est = [140372.0, 273545.4, 0.0, 0.0]
+    neyetr, neyesamp, nfft = 2, 3, 4
+    rx_eye = [[0.5] * 160 for _ in range(8)]
+    samp_fft = [0.25] * 512
+
+
+class _FakeEngine:
+    """stands in for wenet_b200.engine.Engine in the host-logic test below: whole frames of N samples in, Nbits soft
+    decisions / hard bits per frame out (no GPU in the CPU suite; the real thing is in tests/test_gpu_parity.py)"""
+    N, Nbits = 384, 48
+    made = []
+
+    def __init__(self, n, **kw):
+        self.kw, self.pending, self.rest, self.frames, self.blocks = kw, 0, 0, 0, []
+        _FakeEngine.made.append(self)
+
+    def feed(self, arrs):
+        self.rest += arrs[0].size // 2
+        self.blocks.append(arrs[0].size // 2)
+
+    def process(self):
+        self.pending, self.rest = self.rest // self.N, self.rest % self.N
+        self.frames += self.pending
+
+    def sync(self):
+        pass
+
+    def drain_soft(self, s):
+        import numpy as np
+        return np.full(self.pending * self.Nbits, -1.0, dtype=np.float32)
+
+    def drain_hard(self, s):
+        import numpy as np
+        assert self.kw["hard_bits"]
+        return np.ones(self.pending * self.Nbits, dtype=np.uint8)
+
+    def stats(self, s):
+        assert self.kw["stats"]
+        return _FakeStats()
+
+    def close(self):
+        pass
+
+
+def _run_main(monkeypatch, argv, nbytes):
+    import io
+    import sys as _sys
+    from wenet_b200 import engine as E
+    from wenet_b200.cli import fsk_demod as F
+    monkeypatch.setattr(E, "Engine", _FakeEngine)
+    _FakeEngine.made.clear()
+    out, err = io.BytesIO(), io.StringIO()
+    fake_in = type("I", (), {"buffer": io.BytesIO(bytes(nbytes))})()
+    fake_out = type("O", (), {"buffer": out})()
+    monkeypatch.setattr(_sys, "stdin", fake_in)
+    monkeypatch.setattr(_sys, "stdout", fake_out)
+    monkeypatch.setattr(_sys, "stderr", err)
+    assert F.main(["fsk_demod"] + argv) == 0
+    return out.getvalue(), err.getvalue(), _FakeEngine.made[-1]
+
+
+def test_fsk_demod_main_loop_host_logic(monkeypatch):
+    """the stand-in's block loop around a fake engine: output sizes, the reference's stats cadence (--stats=100 at
+    921416 / 384: one JSON line per 24 frames, src/fsk_demod.c:247-251), hard / soft / testframe branches"""
+    import json
+    nframes = 240
+    out, err, eng = _run_main(monkeypatch, ["--cu8", "-s", "--stats=100", "2", "921416", "115177", "-", "-"], nframes * 384 * 2 + 100)
+    assert len(out) == nframes * 48 * 4 and eng.kw["stats"] and not eng.kw["hard_bits"] and eng.kw["in_fmt"] == "cu8"
+    recs = [json.loads(l) for l in err.splitlines()]
+    assert len(recs) == nframes // 24 and set(eng.blocks[:-1]) == {24 * 384}
+    for k in ("secs", "EbNodB", "ppm", "f1_est", "f2_est", "eye_diagram", "samp_fft"):     # rx/fskstatsudp.py:29, :214-226
+        assert k in recs[0], k
+    assert len(recs[0]["samp_fft"]) == 4 and len(recs[0]["eye_diagram"]) == 2 and "f3_est" not in recs[0]
+    # hard-bit output, no stats: 64-frame blocks, one byte per bit from the engine's hard-bit tap
+    out, err, eng = _run_main(monkeypatch, ["--cs16", "4", "921416", "115177", "-", "-"], nframes * 384 * 4)
+    assert out == b"\x01" * (nframes * 48) and err == "" and eng.kw["hard_bits"] and eng.kw["M"] == 4
+    assert eng.blocks[0] == 64 * 384
+    # testframe mode: all-ones bits never match the known frame -> no lines, but the branch runs (soft and hard, with -t)
+    for extra in (["-f"], ["-f", "-s"], ["-f", "-t"], ["-f", "-s", "-t5"]):
+        out, err, eng = _run_main(monkeypatch, ["--cs16"] + extra + ["2", "921416", "115177", "-", "-"], 100 * 384 * 4)
+        assert err == "" and len(out) == 100 * 48 * (4 if "-s" in extra else 1), extra
+
+
+def test_ldpc_cli_main_loop_host_logic(monkeypatch, tmp_path):
+    """drs232_ldpc stand-in around a fake engine: packet bytes out, the reference's per-packet and summary lines
+    (src/drs232_ldpc.c:261-265, :280) with uint16 counters and printf's PER"""
+    import numpy as np
+    from wenet_b200 import engine as E
+    from wenet_b200.cli import _ldpc_cli as L
+
+    class Fake:
+        sd_cap = 1 << 20
+
+        def __init__(self, n, **kw):
+            self.calls = 0
+
+        def process_soft(self, arrs):
+            self.calls += 1
+
+        def sync(self):
+            pass
+
+        def drain_codewords(self):
+            if self.calls != 1:
+                return []
+            return [{"crc_ok": 1, "iters": 2}, {"crc_ok": 0, "iters": 10}, {"crc_ok": 1, "iters": 3}]
+
+        def drain_packets(self, s):
+            return b"\x55" * 512 if self.calls == 1 else b""
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(E, "Engine", Fake)
+    fin, fout = tmp_path / "in.f32", tmp_path / "out.bin"
+    np.zeros(5000, dtype=np.float32).tofile(fin)
+    import io
+    import sys as _sys
+    err = io.StringIO()
+    monkeypatch.setattr(_sys, "stderr", err)
+    assert L.main(["drs232_ldpc", str(fin), str(fout), "-v"], "v1", "drs232") == 0
+    assert fout.read_bytes() == b"\x55" * 512
+    assert err.getvalue() == ("packets: 1 packet_errors: 0 PER: 0.000 iter: 2\n"
+                              "packets: 2 packet_errors: 1 PER: 0.500 iter: 10\n"
+                              "packets: 3 packet_errors: 1 PER: 0.333 iter: 3\n"
+                              "packets: 3 packet_errors: 1 PER: 0.333\n")

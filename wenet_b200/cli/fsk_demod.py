@@ -4,8 +4,8 @@
 Same argv, input formats, output stream and exit codes as reference src/fsk_demod.c:89-206, demodulating on the
 GPU through libwenet_b200.so.  Differences, all outside the hot path: -l (low-rate mode: another frame geometry,
 used by no Wenet script) is not implemented and exits 1; the stats JSON (stderr, -t) has the reference's keys (secs,
-EbNodB, ppm, f1_est, f2_est[, f3_est, f4_est], eye_diagram, samp_fft -- what rx/fskstatsudp.py parses) but is emitted
-per block of frames.  -f (testframe mode, src/fsk_demod.c:226-243, :304-343) counts bit errors against the reference's
+EbNodB, ppm, f1_est, f2_est[, f3_est, f4_est], eye_diagram, samp_fft -- what rx/fskstatsudp.py parses) at the reference's cadence, with
+the statistics as they stand at the end of a block of frames (with -t a block is one stats period).  -f (testframe mode, src/fsk_demod.c:226-243, :304-343) counts bit errors against the reference's
 known frame on the host (wenet_b200/cli/_testframes.py): the same "errs: ..." lines, or with -t one JSON line per modem
 frame that completed a testframe (modem statistics in it are the block's, the frames/bits/errs counters exact).
 Without -s the output is the demodulator's own hard bits (arg-max tone, src/fsk.c:936-959), one byte per bit.
@@ -137,12 +137,15 @@ def main(argv=None):
     dt = E.FMT_DTYPE[o["fmt"]]
     stats_every = int(1 / (o["stats_rate"] * eng.N / o["Fs"])) + 1 if o["stats"] else 0
     frames_since = 0
+    # with -t the blocks shrink to the reference's stats cadence (one JSON line every stats_loop + 1 frames,
+    # src/fsk_demod.c:247-251, :394-400), so that fskstatsudp.py sees as many lines per second as from the reference
+    block_frames = max(1, min(BLOCK_FRAMES, stats_every)) if (o["stats"] and not o["testframes"]) else BLOCK_FRAMES
     tf = None
     if o["testframes"]:
         from wenet_b200.cli._testframes import TestFrames
         tf = TestFrames()
     while True:
-        raw = fin.read(BLOCK_FRAMES * eng.N * bps)
+        raw = fin.read(block_frames * eng.N * bps)
         if not raw:
             break
         raw = raw[:len(raw) - len(raw) % bps]
@@ -177,7 +180,7 @@ def main(argv=None):
         if o["stats"] and sd.size:
             frames_since += sd.size // eng.Nbits
             if frames_since >= stats_every:
-                frames_since = 0
+                frames_since -= stats_every       # nin wanders around N: keep the average cadence
                 st = eng.stats(0)
                 d = {"secs": int(time.time()), "EbNodB": round(st.EbNodB, 1), "ppm": int(st.ppm),
                      "f1_est": round(st.f_est[0], 1), "f2_est": round(st.f_est[1], 1)}
