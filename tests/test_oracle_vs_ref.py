@@ -68,6 +68,17 @@ def test_fsk_4fsk(oracle_port, oracle_ref):
     assert np.array_equal(sa.view(np.uint32), sb.view(np.uint32)) and np.array_equal(la.view(np.uint32), lb.view(np.uint32))
 
 
+@pytest.mark.parametrize("Fs,Rs,P,fmt", [(921416, 115177, 4, "cu8"), (921416, 115177, 2, "cf32"), (960000, 96000, 5, "cs16"),
+                                         (960000, 96000, 10, "cf32")])
+def test_fsk_4fsk_other_geometries(oracle_port, oracle_ref, Fs, Rs, P, fmt):
+    """4-FSK with P < Ts (fsk_demod -p) and at 10 samples per symbol: soft decisions, frame log and hard bits"""
+    raw, _ = siggen.make_4fsk_stream(41, 2500, ebno_db=8.0, fmt=fmt, Fs=Fs, Rs=Rs)
+    a, b = oracle_port.fsk(Fs, Rs, M=4, P=P).run(raw, fmt), oracle_ref.fsk(Fs, Rs, M=4, P=P).run(raw, fmt)
+    assert a[0].size > 4000 and np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32))
+    assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)) and a[2] == b[2]
+    assert np.array_equal(oracle_port.fsk(Fs, Rs, M=4, P=P).run_bits(raw, fmt), oracle_ref.fsk(Fs, Rs, M=4, P=P).run_bits(raw, fmt))
+
+
 @pytest.mark.parametrize("M,fmt,ebno", [(4, "cu8", 4.0), (4, "cf32", 9.0), (2, "cs16", 3.0)])
 def test_fsk_hard_bits(oracle_port, oracle_ref, M, fmt, ebno):
     """rx_bits of fsk_demod() (src/fsk.c:936-959), the output of `fsk_demod` without -s"""
