@@ -73,3 +73,32 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".c")) and f != "wb_tables.h":
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "liboracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_c_example_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/decode_file.c (a plain C99 caller of include/wenet_b200.h, the shape of a program that links the
+    reference's fsk.c / mpdecode_core.c today) compiles with -Wall -Wextra, links against the product library and,
+    where no CUDA device is visible, stops with the library's own message instead of decoding on the CPU"""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "decode_file")
+    libdir = os.path.join(root, "wenet_b200")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"),
+                        os.path.join(root, "examples", "decode_file.c"), "-L" + libdir, "-lwenet_b200",
+                        "-Wl,-rpath," + libdir, "-o", exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()
+    assert subprocess.run([exe], stderr=subprocess.PIPE).returncode == 1            # usage
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return                                                                    # the GPU suite covers the rest
+    except Exception:
+        pass
+    src = tmp_path / "in.cu8"
+    src.write_bytes(bytes(4096))
+    r = subprocess.run([exe, str(src), str(tmp_path / "out.bin")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 2 and b"no CPU fallback" in r.stderr
