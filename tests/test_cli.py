@@ -165,7 +165,9 @@ def test_ldpc_cli_main_loop_host_logic(monkeypatch, tmp_path):
         def drain_codewords(self):
             if self.calls != 1:
                 return []
-            return [{"crc_ok": 1, "iters": 2}, {"crc_ok": 0, "iters": 10}, {"crc_ok": 1, "iters": 3}]
+            bad = np.zeros(258, dtype=np.uint8)
+            bad[256], bad[257] = 0x34, 0x12
+            return [{"crc_ok": 1, "iters": 2}, {"crc_ok": 0, "iters": 10, "bytes": bad}, {"crc_ok": 1, "iters": 3}]
 
         def drain_packets(self, s):
             return b"\x55" * 512 if self.calls == 1 else b""
@@ -182,7 +184,12 @@ def test_ldpc_cli_main_loop_host_logic(monkeypatch, tmp_path):
     monkeypatch.setattr(_sys, "stderr", err)
     assert L.main(["drs232_ldpc", str(fin), str(fout), "-v"], "v1", "drs232") == 0
     assert fout.read_bytes() == b"\x55" * 512
-    assert err.getvalue() == ("packets: 1 packet_errors: 0 PER: 0.000 iter: 2\n"
-                              "packets: 2 packet_errors: 1 PER: 0.500 iter: 10\n"
-                              "packets: 3 packet_errors: 1 PER: 0.333 iter: 3\n"
-                              "packets: 3 packet_errors: 1 PER: 0.333\n")
+    lines = ["packets: 1 packet_errors: 0 PER: 0.000 iter: 2\n", "packets: 2 packet_errors: 1 PER: 0.500 iter: 10\n",
+             "packets: 3 packet_errors: 1 PER: 0.333 iter: 3\n", "packets: 3 packet_errors: 1 PER: 0.333\n"]
+    assert err.getvalue() == "".join(lines)
+    # -vv (what start_rx.sh passes) adds the two checksums of a packet that fails its CRC, src/drs232_ldpc.c:246-251
+    err.seek(0); err.truncate()
+    from wenet_b200.siggen import crc16_ccitt_false
+    assert L.main(["drs232_ldpc", str(fin), str(fout), "-vv"], "v1", "drs232") == 0
+    lines.insert(1, "tx_checksum: 0x1234 rx_checksum: 0x%02x\n" % crc16_ccitt_false(bytes(256)))
+    assert err.getvalue() == "".join(lines)

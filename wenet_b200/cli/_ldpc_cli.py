@@ -27,7 +27,7 @@ def main(argv, framing, name):
     except OSError as e:
         sys.stderr.write("Error opening output file: %s: %s.\n" % (argv[2], e.strerror))
         sys.exit(1)
-    verbose = 1 if (len(argv) > 3 and argv[3] in ("-v", "-vv")) else 0
+    verbose = {"-v": 1, "-vv": 2}.get(argv[3], 0) if len(argv) > 3 else 0
     from wenet_b200 import engine as E
     try:
         eng = E.Engine(1, framing=framing, chunk_samples=BLOCK_SYMS * 16)
@@ -46,6 +46,11 @@ def main(argv, framing, name):
             packets = (packets + 1) & 0xFFFF                     # uint16_t counters, src/drs232_ldpc.c:116
             if not cw["crc_ok"]:
                 errors = (errors + 1) & 0xFFFF
+                if verbose == 2:                                 # src/drs232_ldpc.c:246-251
+                    from wenet_b200.siggen import crc16_ccitt_false
+                    body = bytes(bytearray(cw["bytes"]))
+                    sys.stderr.write("tx_checksum: 0x%02x rx_checksum: 0x%02x\n"
+                                     % (body[256] + (body[257] << 8), crc16_ccitt_false(body[:256])))
             if verbose:
                 sys.stderr.write("packets: %d packet_errors: %d PER: %s iter: %d\n" % (packets, errors, _per(errors, packets), cw["iters"]))
         pk = eng.drain_packets(0)
