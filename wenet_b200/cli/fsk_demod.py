@@ -38,6 +38,13 @@ def usage(prog, msg=None):
     sys.exit(1)
 
 
+def _atoi(text):
+    """C atoi(): optional sign and leading digits, 0 if there are none (the reference parses every number with it)"""
+    import re
+    m = re.match(r"\s*([+-]?\d+)", text or "")
+    return int(m.group(1)) if m else 0
+
+
 def _split_stats_option(args):
     """-t[r] / --stats[=r] takes an OPTIONAL argument (getopt_long "t::", src/fsk_demod.c:92-110), which Python's getopt
     does not know: the value only counts when attached (`-t100`, `--stats=100`, the form every start_rx script uses),
@@ -76,10 +83,7 @@ def parse(argv):
         usage(argv[0], str(e))
     o = dict(fmt="s16", soft=False, stats=stats_on, stats_rate=8, P=0, lo=0, hi=0, testframes=False)
     if stats_rate:
-        try:
-            o["stats_rate"] = int(stats_rate) or 8        # atoi() == 0 -> 8, src/fsk_demod.c:126-129
-        except ValueError:
-            o["stats_rate"] = 8
+        o["stats_rate"] = _atoi(stats_rate) or 8          # atoi() == 0 -> 8, src/fsk_demod.c:126-129
     for k, v in opts:
         if k in ("-h", "--help"):
             usage(argv[0])
@@ -94,11 +98,11 @@ def parse(argv):
         elif k in ("-s", "--soft-dec"):
             o["soft"] = True
         elif k in ("-p", "--conv"):
-            o["P"] = int(v)
+            o["P"] = _atoi(v)
         elif k in ("-b", "--fsk_lower"):
-            o["lo"] = int(v or 0)
+            o["lo"] = _atoi(v)
         elif k in ("-u", "--fsk_upper"):
-            o["hi"] = int(v or 0)
+            o["hi"] = _atoi(v)
     if len(args) < 5:
         usage(argv[0], "Too few arguments")
     if len(args) > 5:
