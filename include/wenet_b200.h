@@ -123,7 +123,10 @@ int  wb_sync(wb_engine *e);
 /* the fwrite(packet) of drs232_ldpc.c:254: CRC-valid 256-byte payloads of `stream`, decode order,
    produced since the last drain of that stream */
 int  wb_drain_packets(wb_engine *e, int stream, uint8_t *buf, size_t cap, size_t *nbytes);
-/* every stream at once: records of {int32 stream, uint32 seq, 256 bytes}, sorted by (stream, seq) */
+/* every stream at once: records of {int32 stream, uint32 seq, 256 bytes}, sorted by (stream, seq); seq is the
+   per-stream codeword number the payload came from (= wb_codeword.seq: it keeps counting across calls, and CRC
+   failures leave gaps), so (stream, seq) is unique for the life of the engine.  The per-stream queues behind
+   wb_drain_packets / wb_drain_all_packets grow until drained. */
 int  wb_drain_all_packets(wb_engine *e, uint8_t *buf, size_t cap, size_t *nbytes, uint64_t *npackets);
 /* the fwrite(sdbuf) of fsk_demod.c:403: soft decisions of `stream` produced by the LAST wb_process */
 int  wb_drain_soft(wb_engine *e, int stream, float *buf, size_t cap_floats, size_t *n);

@@ -4,6 +4,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -193,3 +195,53 @@ def test_ldpc_cli_main_loop_host_logic(monkeypatch, tmp_path):
     assert L.main(["drs232_ldpc", str(fin), str(fout), "-vv"], "v1", "drs232") == 0
     lines.insert(1, "tx_checksum: 0x1234 rx_checksum: 0x%02x\n" % crc16_ccitt_false(bytes(256)))
     assert err.getvalue() == "".join(lines)
+
+
+def test_fsk_demod_numbers_parse_like_atoi():
+    """Mode / SampleRate / SymbolRate go through atoi() in the reference (src/fsk_demod.c:181-183), and a bare
+    --fsk_lower / --fsk_upper (optional_argument without a value, :97-98) is accepted and ignored"""
+    from wenet_b200.cli import fsk_demod as F
+    o = F.parse(["fsk_demod", "--cu8", "-s", "--fsk_lower", "--fsk_upper", "2", "921416Hz", " 115177", "-", "-"])
+    assert (o["M"], o["Fs"], o["Rs"], o["lo"], o["hi"]) == (2, 921416, 115177, 0, 0)
+    with pytest.raises(SystemExit) as ex:
+        F.parse(["fsk_demod", "two", "921416", "115177", "-", "-"])      # atoi("two") = 0: not a valid mode, exit(1)
+    assert ex.value.code == 1
+
+
+def test_stats_line_feeds_the_reference_relay_parser():
+    """the stand-in's stderr JSON line goes through the UNMODIFIED rx/fskstatsudp.py FSKDemodStats.update
+    (the parser between fsk_demod's stderr and wenetserver.py's UDP port) and comes out as snr / ppm / fest / fft_db"""
+    import importlib.util
+    import os
+    import sys
+    import types
+    ref = "/root/reference/rx/fskstatsudp.py"
+    if not os.path.exists(ref):
+        pytest.skip("needs the reference tree")
+    from wenet_b200 import engine as E
+    from wenet_b200.cli import fsk_demod as F
+    st = E.WbStats()
+    st.EbNodB, st.ppm = 11.26, -37.9
+    st.f_est[0], st.f_est[1] = 140372.3, 259148.2
+    st.neyetr, st.neyesamp, st.nfft = 8, 16, 128
+    for i in range(8):
+        for j in range(16):
+            st.rx_eye[i][j] = float("nan") if (i, j) == (0, 0) else (i + j) / 23.0     # the reference prints nan there too
+    for k in range(128):
+        st.samp_fft[k] = 0.001 * k
+    line = F.stats_line(st, 2)
+    sys.modules.setdefault("WenetPackets", types.SimpleNamespace(WENET_IMAGE_UDP_PORT=7890))   # its only import from rx/
+    spec = importlib.util.spec_from_file_location("ref_fskstatsudp", ref)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    p = mod.FSKDemodStats(averaging_time=5.0, peak_hold=True, freq=441200000, sample_rate=921416)
+    errors = []
+    p.log_error = errors.append
+    p.update(line)
+    assert not errors, errors
+    assert abs(p.snr - 11.3) < 1e-9 and p.ppm == -37 and p.fest == [140372.3, 259148.2]
+    assert len(p.fft_db) == 128 and len(p.fft_freq) == 128 and abs(p.fcentre - (441200000 + (140372.3 + 259148.2) / 2)) < 1e-6
+    # 4-FSK adds f3_est / f4_est, which the parser ignores
+    st.f_est[2], st.f_est[3] = 300000.0, 400000.0
+    p.update(F.stats_line(st, 4))
+    assert not errors

@@ -591,3 +591,86 @@ def test_general_P_vs_oracle(eng_mod, oracle_port, cfg, P, fmt):
     assert np.array_equal(sd_g.view(np.uint32), sd_o.view(np.uint32))
     assert e.drain_packets(0) == res_o["packets"]
     e.close()
+
+
+def test_c_example_decodes_the_golden_stream(tmp_path):
+    """examples/decode_file.c -- a plain C99 caller, no Python between it and the C ABI -- compiled, RUN on the GPU
+    on the reference's own input (tests/golden/fsk_v1.npz: cu8 IQ) and compared with the packets the reference
+    binaries wrote for it"""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "decode_file")
+    libdir = os.path.join(root, "wenet_b200")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "examples", "decode_file.c"), "-L" + libdir, "-lwenet_b200",
+                    "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    z = np.load(os.path.join(GOLD, "fsk_v1.npz"))
+    src, dst = tmp_path / "in.cu8", tmp_path / "out.bin"
+    src.write_bytes(z["raw"].tobytes())
+    r = subprocess.run([exe, str(src), str(dst)], stderr=subprocess.PIPE, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()
+    assert dst.read_bytes() == z["packets"].tobytes()
+    assert b"packets: 2" in r.stderr
+    # and through a pipe, the way start_rx.sh runs the reference (stdin -> stdout)
+    r = subprocess.run([exe, "-", "-"], input=z["raw"].tobytes(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert r.returncode == 0 and r.stdout == z["packets"].tobytes()
+
+
+def test_drain_all_packets_seq_is_the_codeword_number(eng_mod, oracle_port):
+    """(stream, seq) of wb_drain_all_packets is unique for the life of the engine: seq = wb_codeword.seq of the codeword
+    the payload came from, counting on across calls, with a gap where a codeword failed its CRC"""
+    cfg = siggen.V1
+    raws = [siggen.make_stream(300 + s, n_packets=5, ebno_db=eb, fmt="cf32")[0] for s, eb in enumerate((12.0, 6.5, 12.0))]
+    n = max(r.size for r in raws) // 2
+    e = eng_mod.Engine(3, in_fmt="cf32", framing="v1", chunk_samples=n // 2 + 2048)
+    seen, cws = [], []
+    for half in range(2):
+        e.feed([r[:2 * (n // 2)] if half == 0 else r[2 * (n // 2):] for r in raws])
+        e.process()
+        e.sync()
+        cws.append(e.drain_codewords())
+        seen.append(e.drain_all_packets())
+    pk = np.concatenate(seen)
+    cw = np.concatenate(cws)
+    assert len(seen[0]) and len(seen[1])
+    keys = list(zip(pk["stream"].tolist(), pk["seq"].tolist()))
+    assert len(set(keys)) == len(keys)                                     # no duplicate (stream, seq) across drains
+    good = cw[cw["crc_ok"] == 1]
+    assert sorted(keys) == sorted(zip(good["stream"].tolist(), good["seq"].tolist()))
+    for part in seen:                                                      # each call: sorted by (stream, seq)
+        k = list(zip(part["stream"].tolist(), part["seq"].tolist()))
+        assert k == sorted(k)
+    for s in range(3):
+        want = oracle_port.deframer("v1", 10).feed(oracle_port.fsk(cfg["Fs"], cfg["Rs"]).run(raws[s], "cf32")[0])
+        assert pk["payload"][pk["stream"] == s].tobytes() == want["packets"], s
+        assert cw["seq"][cw["stream"] == s].tolist() == list(range(len(want["iters"]))), s
+    e.close()
+
+
+def test_process_soft_between_feed_and_process_keeps_the_fed_samples(eng_mod, oracle_port):
+    """the ABI allows wb_feed, wb_process_soft, wb_feed, wb_process on one engine: the soft-only pass consumes no IQ
+    samples, so what was fed before it must still be demodulated afterwards"""
+    cfg = siggen.V1
+    raw, _ = siggen.make_stream(77, n_packets=3, ebno_db=11.0, fmt="cf32")
+    n = raw.size // 2
+    sd_o = oracle_port.fsk(cfg["Fs"], cfg["Rs"]).run(raw, "cf32")[0]
+    e = eng_mod.Engine(1, in_fmt="cf32", framing="v1", chunk_samples=n + 2048)
+    a = (n // 3) & ~1
+    e.feed([raw[:2 * a]])
+    e.process()
+    e.sync()
+    got = [e.drain_soft(0)]
+    e.feed([raw[2 * a:2 * 2 * a]])
+    e.process_soft([np.zeros(100, dtype=np.float32)])       # a deframer-only pass in between
+    e.sync()
+    e.feed([raw[2 * 2 * a:]])
+    e.process()
+    e.sync()
+    got.append(e.drain_soft(0))
+    g = np.concatenate(got)
+    assert g.size == sd_o.size and np.array_equal(g.view(np.uint32), sd_o.view(np.uint32))
+    e.close()

@@ -153,15 +153,12 @@ def test_edge_cases(E, oracle_port):
     e.close()
 
 
-# Last in the GPU suite on purpose.  The four 4-FSK instantiations below (P < Ts, and 10 samples per symbol) come from
-# the same kernel template as the tested ones and the oracle is pinned for them against the compiled reference
-# (tests/test_oracle_vs_ref.py::test_fsk_4fsk_other_geometries), but the round's GPU budget ended before their first run
-# on a B200.  xfail(strict=False): an XPASS in the summary line means they are verified, an xfail means they are not yet;
-# either way the result is reported without standing in for a claim.  Remove the marker once they have been seen to pass.
-@pytest.mark.xfail(strict=False, reason="first run of these kernel instantiations on a B200; see the comment above")
+# The four remaining 4-FSK instantiations of the kernel template (P < Ts, and 10 samples per symbol); the oracle is
+# pinned for them against the compiled reference (tests/test_oracle_vs_ref.py::test_fsk_4fsk_other_geometries).  First seen
+# to pass on a B200 by the round-1 driver run (XPASS x4 in GPUTEST_r01.json); a regression now fails the suite.
 @pytest.mark.parametrize("Fs,Rs,P,fmt", [(921416, 115177, 4, "cu8"), (921416, 115177, 2, "cf32"), (960000, 96000, 5, "cs16"),
                                          (960000, 96000, 10, "cf32")])
-def test_4fsk_other_geometries_first_run(E, oracle_port, Fs, Rs, P, fmt):
+def test_4fsk_other_geometries(E, oracle_port, Fs, Rs, P, fmt):
     raws = [siggen.make_4fsk_stream(41 + s, 2500, ebno_db=6.0 + 3 * s, fmt=fmt, Fs=Fs, Rs=Rs)[0] for s in range(3)]
     per = E.FMT_ELEMS[fmt]
     e = E.Engine(3, Fs=Fs, Rs=Rs, M=4, P=P, in_fmt=fmt, framing="none", chunk_samples=raws[0].size // per + 1024,

@@ -35,11 +35,19 @@ def main(argv, framing, name):
         sys.stderr.write("%s\n" % e)
         sys.exit(1)
     packets = errors = 0
+    # a pipe hands over whatever has arrived (read1), so a packet is decoded as soon as its last symbol is there, as in
+    # the reference's per-symbol loop; a regular file comes in full blocks.  A split float waits for its other half.
+    read = getattr(fin, "read1", fin.read)
+    left = b""
     while True:
-        raw = fin.read(4 * min(BLOCK_SYMS, eng.sd_cap))
+        raw = read(4 * min(BLOCK_SYMS, eng.sd_cap))
         if not raw:
             break
-        raw = raw[:len(raw) - len(raw) % 4]
+        raw = left + raw
+        left = raw[len(raw) - len(raw) % 4:]
+        raw = raw[:len(raw) - len(left)]
+        if not raw:
+            continue
         eng.process_soft([np.frombuffer(raw, dtype=np.float32)])
         eng.sync()
         for cw in eng.drain_codewords():

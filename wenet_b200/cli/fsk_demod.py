@@ -13,6 +13,7 @@ Output is written per block of frames, not per frame.
 """
 import getopt
 import json
+import math
 import signal
 import sys
 import time
@@ -58,6 +59,8 @@ def _split_stats_option(args):
             continue
         if a == "--stats" or a.startswith("--stats="):
             enabled, rate = True, (a[8:] if a.startswith("--stats=") else None)
+            continue
+        if a in ("--fsk_lower", "--fsk_upper"):   # optional_argument without a value: accepted and ignored (optarg NULL)
             continue
         if not a.startswith("--"):
             k = 1
@@ -107,14 +110,25 @@ def parse(argv):
         usage(argv[0], "Too few arguments")
     if len(args) > 5:
         usage(argv[0], "Too many arguments")
-    try:
-        o["M"], o["Fs"], o["Rs"] = int(args[0]), int(args[1]), int(args[2])
-    except ValueError:
-        usage(argv[0], "Mode, SampleRate and SymbolRate must be integers")
+    o["M"], o["Fs"], o["Rs"] = _atoi(args[0]), _atoi(args[1]), _atoi(args[2])      # atoi(), src/fsk_demod.c:181-183
     if o["M"] not in (2, 4):
         usage(argv[0], "Mode %d is not valid. Mode must be 2 or 4." % o["M"])
     o["fin"], o["fout"] = args[3], args[4]
     return o
+
+
+def stats_line(st, M):
+    """One stderr line of the reference's `-t` / `--stats` output (src/fsk_demod.c:345-392) from a wb_stats record:
+    the keys rx/fskstatsudp.py requires (EbNodB, ppm, f1_est, f2_est, samp_fft) plus eye_diagram and, for 4-FSK,
+    f3_est / f4_est."""
+    ppm = int(st.ppm) if math.isfinite(st.ppm) else 0           # C's (int) of a non-finite float does not raise
+    d = {"secs": int(time.time()), "EbNodB": round(st.EbNodB, 1), "ppm": ppm,
+         "f1_est": round(st.f_est[0], 1), "f2_est": round(st.f_est[1], 1)}
+    if M == 4:
+        d["f3_est"], d["f4_est"] = round(st.f_est[2], 1), round(st.f_est[3], 1)
+    d["eye_diagram"] = [[round(float(st.rx_eye[i][j]), 6) for j in range(st.neyesamp)] for i in range(st.neyetr)]
+    d["samp_fft"] = [round(float(v), 6) for v in st.samp_fft[:st.nfft]]
+    return json.dumps(d)
 
 
 def main(argv=None):
@@ -148,11 +162,19 @@ def main(argv=None):
     if o["testframes"]:
         from wenet_b200.cli._testframes import TestFrames
         tf = TestFrames()
+    # a pipe hands over whatever has arrived (read1): frames go out as soon as their samples are in, like the reference's
+    # per-frame fread/fwrite; a regular file comes in full blocks.  A split sample waits for its other half.
+    read = getattr(fin, "read1", fin.read)
+    left = b""
     while True:
-        raw = fin.read(block_frames * eng.N * bps)
+        raw = read(block_frames * eng.N * bps)
         if not raw:
             break
-        raw = raw[:len(raw) - len(raw) % bps]
+        raw = left + raw
+        left = raw[len(raw) - len(raw) % bps:]
+        raw = raw[:len(raw) - len(left)]
+        if not raw:
+            continue
         eng.feed([np.frombuffer(raw, dtype=dt)])
         eng.process()
         eng.sync()
@@ -176,7 +198,7 @@ def main(argv=None):
                     last[h[0] // eng.Nbits] = h
                 for h in last.values():
                     d = '{"secs": %d, "EbNodB": %5.1f, "ppm": %4d, "f1_est":%.1f, "f2_est":%.1f' % (
-                        int(time.time()), st.EbNodB, int(st.ppm), st.f_est[0], st.f_est[1])
+                        int(time.time()), st.EbNodB, int(st.ppm) if math.isfinite(st.ppm) else 0, st.f_est[0], st.f_est[1])
                     if o["M"] == 4:
                         d += ', "f3_est":%.1f, "f4_est":%.1f' % (st.f_est[2], st.f_est[3])
                     sys.stderr.write(d + ', "frames":%d, "bits":%d, "errs":%d}\n' % (h[2], h[3], h[4]))
@@ -185,15 +207,7 @@ def main(argv=None):
             frames_since += sd.size // eng.Nbits
             if frames_since >= stats_every:
                 frames_since -= stats_every       # nin wanders around N: keep the average cadence
-                st = eng.stats(0)
-                d = {"secs": int(time.time()), "EbNodB": round(st.EbNodB, 1), "ppm": int(st.ppm),
-                     "f1_est": round(st.f_est[0], 1), "f2_est": round(st.f_est[1], 1)}
-                if o["M"] == 4:
-                    d["f3_est"], d["f4_est"] = round(st.f_est[2], 1), round(st.f_est[3], 1)
-                d["eye_diagram"] = [[round(float(st.rx_eye[i][j]), 6) for j in range(st.neyesamp)]
-                                    for i in range(st.neyetr)]
-                d["samp_fft"] = [round(float(v), 6) for v in st.samp_fft[:st.nfft]]
-                sys.stderr.write(json.dumps(d) + "\n")
+                sys.stderr.write(stats_line(eng.stats(0), o["M"]) + "\n")
     fout.flush()
     eng.close()
     return 0

@@ -65,7 +65,7 @@ struct wb_engine {
     wb_cursor *d_cursor;
     float *d_sd;
     unsigned char *d_hard;           /* WB_FLAG_HARD_BITS */
-    bool hard_valid;                 /* the last process call ran the demodulator */
+    bool hard_valid;                 /* the last process call ran the demodulator (wb_process, not wb_process_soft) */
     unsigned long long sd_stride;
     unsigned sd_cap;
     unsigned *d_jobs;
@@ -93,8 +93,9 @@ struct wb_engine {
     std::vector<wb_cursor> cursor;                 /* as of the last wb_sync */
     std::vector<unsigned long long> fill;          /* samples resident per stream (host's view) */
     std::vector<int> nin;
-    struct pktq { std::vector<uint8_t> buf; size_t rd = 0; size_t size() const { return buf.size() - rd; }
-                  void clear() { buf.clear(); rd = 0; } };
+    /* payload bytes and, packet for packet, the codeword sequence number (wb_codeword.seq) they came from */
+    struct pktq { std::vector<uint8_t> buf; std::vector<uint32_t> seqs; size_t rd = 0; size_t size() const { return buf.size() - rd; }
+                  void clear() { buf.clear(); seqs.clear(); rd = 0; } };
     std::vector<pktq> packets;                     /* CRC-valid payloads not yet drained, per stream */
     std::vector<wb_codeword> last_cw;              /* codewords of the last wb_process, (stream, seq) order */
     std::vector<float> last_llr;
@@ -788,7 +789,9 @@ static int wb_collect(wb_engine *e)
         if (e->cfg.framing == WB_FRAMING_NONE) e->cursor[s].n_jobs = 0;
         total += e->cursor[s].n_jobs;
         samples += e->cursor[s].consumed;
-        if (!e->resident_mode) e->fill[s] = e->cursor[s].in_fill;
+        /* only a pass that ran the demodulator consumed IQ samples: after wb_process_soft the samples fed since the last
+           wb_process are still waiting in the row (cursor.in_fill is the OLD parked remainder there) */
+        if (!e->resident_mode && e->hard_valid) e->fill[s] = e->cursor[s].in_fill;
         e->nin[s] = e->cursor[s].nin;
     }
     offs[n] = (unsigned)total;
@@ -809,7 +812,11 @@ static int wb_collect(wb_engine *e)
         CU(cudaStreamSynchronize(e->stream));
         for (size_t i = 0; i < total; i++) {
             const wb_codeword &c = e->last_cw[i];
-            if (c.crc_ok) { auto &q = e->packets[c.stream].buf; q.insert(q.end(), c.bytes, c.bytes + WB_PACKET_BYTES); }
+            if (c.crc_ok) {
+                auto &q = e->packets[c.stream];
+                q.buf.insert(q.buf.end(), c.bytes, c.bytes + WB_PACKET_BYTES);
+                q.seqs.push_back(c.seq);
+            }
         }
     }
     return WB_OK;
@@ -853,13 +860,13 @@ extern "C" int wb_drain_all_packets(wb_engine *e, uint8_t *buf, size_t cap, size
     size_t o = 0; uint64_t np = 0;
     for (int s = 0; s < e->cfg.n_streams; s++) {
         wb_engine::pktq &q = e->packets[s];
-        uint32_t k = 0;
         while (q.size() >= WB_PACKET_BYTES) {
-            int32_t ss = s;
+            const int32_t ss = s;
+            const uint32_t k = q.seqs[q.rd / WB_PACKET_BYTES];     /* = wb_codeword.seq of the codeword it came from */
             memcpy(buf + o, &ss, 4); memcpy(buf + o + 4, &k, 4);
             memcpy(buf + o + 8, q.buf.data() + q.rd, WB_PACKET_BYTES);
             q.rd += WB_PACKET_BYTES;
-            o += rec; k++; np++;
+            o += rec; np++;
         }
         q.clear();
     }
