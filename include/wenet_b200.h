@@ -208,6 +208,13 @@ uint64_t wb_last_samples(wb_engine *e);
 /* pinned host memory for staging buffers handed to wb_feed / wb_feed_strided */
 void *wb_host_alloc(size_t bytes);
 void  wb_host_free(void *p);
+/* the pinned-host <-> device copy leg alone (what bounds the host-buffer path end to end): `bytes` of pinned and of
+   device memory on `device`; run = `iters` flat copies back to back, *ms = their CUDA-event duration.  Run on all GPUs of a
+   box at once it gives the box's concurrent-copy ceiling (tools/micro/pcie_multi.cu is the stand-alone form). */
+typedef struct wb_copy_probe wb_copy_probe;
+int  wb_copy_probe_create(int device, size_t bytes, wb_copy_probe **out);
+int  wb_copy_probe_run(wb_copy_probe *p, int iters, int d2h, float *ms);
+void wb_copy_probe_destroy(wb_copy_probe *p);
 /* derived geometry: out[0..13] = N, Nbits, Ts, P, Ndft, nmax, job_cap, sd_cap, Nsym, M, ldpc_max_iter,
    symbols collected per packet, streams per CTA and shared-memory bytes per CTA of the demodulator kernel */
 int  wb_geometry(wb_engine *e, int32_t *out, int n);

@@ -674,3 +674,52 @@ def test_process_soft_between_feed_and_process_keeps_the_fed_samples(eng_mod, or
     g = np.concatenate(got)
     assert g.size == sd_o.size and np.array_equal(g.view(np.uint32), sd_o.view(np.uint32))
     e.close()
+
+
+def _device_count():
+    import ctypes
+    try:
+        rt = ctypes.CDLL("libcudart.so")
+    except OSError:
+        try:
+            rt = ctypes.CDLL("/usr/local/cuda/lib64/libcudart.so")
+        except OSError:
+            return 1
+    n = ctypes.c_int(0)
+    return n.value if rt.cudaGetDeviceCount(ctypes.byref(n)) == 0 else 1
+
+
+def test_multi_engine_equals_one_engine(eng_mod, oracle_port):
+    """MultiEngine (one engine + one feeder thread per slot; slots = every visible GPU, or two engines on GPU 0 on a
+    one-GPU box; weighted placement) against a single engine and the oracle on the same global block: same packets under
+    the same global stream numbers, same soft decisions"""
+    from wenet_b200.multi import MultiEngine
+    cfg = siggen.V1
+    n = 7
+    raws = [siggen.make_stream(600 + s, n_packets=2, ebno_db=7.0 + s, fmt="cu8", clock_ppm=float(300 * (s - 3)))[0] for s in range(n)]
+    nsamp = min(r.size for r in raws) // 2
+    ndev = _device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0]
+    me = MultiEngine(n, devices=devices, weights=[1.0 + 0.5 * (i % 2) for i in range(len(devices))], in_fmt="cu8", framing="v1",
+                     chunk_samples=nsamp + 1024)
+    pb = me.pinned_block(nsamp)
+    for s in range(n):
+        pb.array[s, :] = raws[s][:2 * nsamp]
+    me.step(pb.array)
+    me.sync()
+    pk = me.drain_all_packets()
+    one = eng_mod.Engine(n, in_fmt="cu8", framing="v1", chunk_samples=nsamp + 1024)
+    one.feed_strided(pb.array)
+    one.process()
+    one.sync()
+    pk1 = one.drain_all_packets()
+    assert len(pk) and np.array_equal(pk["stream"], pk1["stream"]) and np.array_equal(pk["seq"], pk1["seq"])
+    assert np.array_equal(pk["payload"], pk1["payload"])
+    assert me.last_samples == one.last_samples and len({g.device for g in me.engines}) == min(ndev, len(devices))
+    for s in range(n):
+        sd_o = oracle_port.fsk(cfg["Fs"], cfg["Rs"]).run(raws[s][:2 * nsamp], "cu8")[0]
+        assert np.array_equal(me.drain_soft(s).view(np.uint32), sd_o.view(np.uint32)), s
+        want = oracle_port.deframer("v1", 10).feed(sd_o)["packets"]
+        assert pk["payload"][pk["stream"] == s].tobytes() == want, s
+    one.close()
+    me.close()

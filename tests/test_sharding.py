@@ -80,3 +80,85 @@ def test_two_ranks_equal_one(oracle_port):
         pk = oracle_port.deframer("v1", 10).feed(sd)["packets"]
         want.append(int(np.frombuffer(pk, np.uint8).astype(np.int64).sum()))
     assert total == n_streams and digest == want and tmax == 2.0
+
+
+def test_weighted_ranges():
+    """blocks in proportion to what each GPU can take; sizes add up exactly, within one stream of the exact share"""
+    for n, w in ((32768, [23.3] * 4 + [35.3] * 4), (10, [1, 1, 1]), (7, [5, 0.5, 1.5]), (4096, [1.0])):
+        r = sharding.weighted_ranges(n, w)
+        assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        for (lo, hi), x in zip(r, w):
+            assert abs((hi - lo) - n * x / sum(w)) < 1.0
+    r = sharding.weighted_ranges(32768, [23.3] * 4 + [35.3] * 4)
+    assert [hi - lo for lo, hi in r[:4]] == [3257] * 4 or sum(hi - lo for lo, hi in r[:4]) in (13028, 13029)
+    assert sharding.equal_ranges(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    with pytest.raises(ValueError):
+        sharding.weighted_ranges(8, [0, 0])
+
+
+class _FakeEngine:
+    """stands in for one GPU: remembers what it was fed, 'decodes' one packet per stream whose payload names the stream"""
+    made = []
+
+    def __init__(self, n_streams, device=0, **kw):
+        self.n_streams, self.device, self.kw = n_streams, device, kw
+        self.fed, self.steps = None, 0
+        _FakeEngine.made.append(self)
+
+    def feed_strided(self, block):
+        assert block.shape[0] == self.n_streams
+        self.fed = block
+
+    def process(self):
+        self.steps += 1
+
+    def sync(self):
+        pass
+
+    def drain_all_packets(self):
+        dt = np.dtype([("stream", "<i4"), ("seq", "<u4"), ("payload", "u1", (256,))])
+        out = np.zeros(self.n_streams, dtype=dt)
+        out["stream"] = np.arange(self.n_streams)
+        out["seq"] = self.steps - 1
+        out["payload"][:, 0] = self.fed[:, 0]              # first byte of what this stream was fed
+        return out
+
+    def drain_soft(self, s):
+        return np.full(3, float(self.fed[s, 0]), dtype=np.float32)
+
+    def nin(self):
+        return np.full(self.n_streams, 384, dtype=np.uint32)
+
+    last_samples = 10
+    last_codewords = 1
+    launch_count = 5
+
+    def close(self):
+        pass
+
+
+def test_multi_engine_places_feeds_and_gathers():
+    """the multi-GPU host object with fake engines: contiguous placement (equal and weighted), each engine is fed its own
+    rows of the global block from its own thread, packets come back under global stream numbers"""
+    from wenet_b200.multi import MultiEngine
+    _FakeEngine.made.clear()
+    n = 11
+    block = np.zeros((n, 8), dtype=np.uint8)
+    block[:, 0] = np.arange(n) + 100
+    me = MultiEngine(n, devices=[0, 1, 2], engine_cls=_FakeEngine, in_fmt="cu8", framing="v1")
+    assert [g.n_streams for g in me.engines] == [4, 4, 3] and [g.device for g in me.engines] == [0, 1, 2]
+    assert me.engines[0].kw == {"in_fmt": "cu8", "framing": "v1"}
+    me.step(block)
+    me.sync()
+    pk = me.drain_all_packets()
+    assert pk["stream"].tolist() == list(range(n)) and pk["payload"][:, 0].tolist() == (np.arange(n) + 100).tolist()
+    assert [me.owner(s) for s in (0, 3, 4, 8, 10)] == [(0, 0), (0, 3), (1, 0), (2, 0), (2, 2)]
+    assert me.drain_soft(9)[0] == 109.0 and me.nin().size == n
+    assert me.last_samples == 30 and me.launch_count == 15
+    me.close()
+    # weighted, two engines per device
+    me = MultiEngine(12, devices=[0, 1], weights=[1.0, 2.0], engines_per_device=2, engine_cls=_FakeEngine)
+    assert [g.n_streams for g in me.engines] == [2, 2, 4, 4] and [g.device for g in me.engines] == [0, 0, 1, 1]
+    me.close()
+    with pytest.raises(ValueError):
+        MultiEngine(2, devices=[0, 1, 2], engine_cls=_FakeEngine)

@@ -1274,6 +1274,65 @@ extern "C" void *wb_host_alloc(size_t bytes)
 }
 extern "C" void wb_host_free(void *p) { if (p) cudaFreeHost(p); }
 
+/* ---- host <-> device copy probe ------------------------------------------
+   The host-buffer path (wb_feed / wb_feed_strided from pinned memory) can go no faster than the PCIe / host-bridge leg;
+   this measures that leg alone: `bytes` of pinned host memory and of device memory, flat cudaMemcpyAsync, CUDA events. */
+struct wb_copy_probe { int device; size_t bytes; unsigned char *h, *d; cudaStream_t s; cudaEvent_t e0, e1; };
+
+extern "C" void wb_copy_probe_destroy(wb_copy_probe *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->s) cudaStreamSynchronize(p->s);
+    if (p->h) cudaFreeHost(p->h);
+    if (p->d) cudaFree(p->d);
+    if (p->e0) cudaEventDestroy(p->e0);
+    if (p->e1) cudaEventDestroy(p->e1);
+    if (p->s) cudaStreamDestroy(p->s);
+    delete p;
+}
+
+extern "C" int wb_copy_probe_create(int device, size_t bytes, wb_copy_probe **out)
+{
+    if (!out || bytes == 0) return wb_fail(WB_EINVAL, "bad argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return wb_fail(WB_ENODEV, "no CUDA device visible");
+    if (device < 0 || device >= ndev) return wb_fail(WB_EINVAL, "device %d of %d", device, ndev);
+    CU(cudaSetDevice(device));
+    wb_copy_probe *p = new wb_copy_probe();
+    memset(p, 0, sizeof(*p));
+    p->device = device; p->bytes = bytes;
+    if (cudaHostAlloc(&p->h, bytes, cudaHostAllocDefault) != cudaSuccess || cudaMalloc(&p->d, bytes) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&p->s, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&p->e0) != cudaSuccess ||
+        cudaEventCreate(&p->e1) != cudaSuccess) {
+        wb_copy_probe_destroy(p);
+        return wb_fail(WB_ENOMEM, "copy probe: allocation of %zu bytes failed", bytes);
+    }
+    memset(p->h, 1, bytes);                                        /* touch every page */
+    if (cudaMemcpyAsync(p->d, p->h, bytes, cudaMemcpyHostToDevice, p->s) != cudaSuccess || cudaStreamSynchronize(p->s) != cudaSuccess) {
+        wb_copy_probe_destroy(p);
+        return wb_fail(WB_ECUDA, "copy probe: warm-up copy failed");
+    }
+    *out = p;
+    return WB_OK;
+}
+
+extern "C" int wb_copy_probe_run(wb_copy_probe *p, int iters, int d2h, float *ms)
+{
+    if (!p || !ms || iters <= 0) return wb_fail(WB_EINVAL, "bad argument");
+    CU(cudaSetDevice(p->device));
+    CU(cudaEventRecord(p->e0, p->s));
+    for (int i = 0; i < iters; i++) {
+        if (d2h) CU(cudaMemcpyAsync(p->h, p->d, p->bytes, cudaMemcpyDeviceToHost, p->s));
+        else CU(cudaMemcpyAsync(p->d, p->h, p->bytes, cudaMemcpyHostToDevice, p->s));
+    }
+    CU(cudaEventRecord(p->e1, p->s));
+    CU(cudaEventSynchronize(p->e1));
+    CU(cudaEventElapsedTime(ms, p->e0, p->e1));
+    return WB_OK;
+}
+
 /* geometry the host wrapper needs */
 extern "C" int wb_geometry(wb_engine *e, int32_t *out, int n)
 {

@@ -68,7 +68,67 @@ __device__ __forceinline__ int wb_cw_symbol(int framing, int c)
 /* ---- K3: sd_to_llr statistics, one thread per codeword --------------------
  * reference src/mpdecode_core.c:577-593.  The two running sums are sequential double additions in
  * the reference; their order is kept (bit-exact LLRs) by giving each codeword to one thread and
- * running thousands of codewords side by side. */
+ * running thousands of codewords side by side.  The kernel is latency bound (one dependent DADD per element and
+ * chain, a double division per element), so the elements are taken eight at a time -- one received byte: eight
+ * adjacent symbols of the row -- with the eight loads and the eight divisions in flight together and only the
+ * additions in element order.  Two passes over the row are inherent (the mean comes before the first x). */
+template <int FRAMING>
+__device__ __forceinline__ void wb_llr_stats_load8(const float *row, int k, const uint8_t *scramble, double v[8])
+{
+    /* elements 8k .. 8k+7 of the codeword; v1: symbols 10k+8 .. 10k+1 (wb_cw_symbol), v2: 8k .. 8k+7 descrambled */
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        if (FRAMING == WB_FRAMING_V1) v[j] = (double)row[10 * k + 8 - j];
+        else {
+            const int c = 8 * k + j;
+            double t = (double)row[c];
+            if (FRAMING == WB_FRAMING_V2 && scramble[c % WB_SCRAMBLE_LEN]) t = -t;
+            v[j] = t;
+        }
+    }
+}
+
+template <int FRAMING>
+__device__ __forceinline__ double wb_llr_stats_row(const float *row, const uint8_t *scramble)
+{
+    constexpr int n = WB_NCODE, NB = n / 8, TAIL = n - 8 * NB;
+    double sum = 0.0, sumsq = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < NB; k++) {
+        double v[8];
+        wb_llr_stats_load8<FRAMING>(row, k, scramble, v);
+#pragma unroll
+        for (int j = 0; j < 8; j++) sum += fabs(v[j]);
+    }
+    {
+        double v[8];
+        wb_llr_stats_load8<FRAMING>(row, NB, scramble, v);       /* the row holds >= 2584 symbols: in bounds */
+#pragma unroll
+        for (int j = 0; j < TAIL; j++) sum += fabs(v[j]);
+    }
+    const double mean = sum / (double)n;
+    sum = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < NB; k++) {
+        double v[8], x[8];
+        wb_llr_stats_load8<FRAMING>(row, k, scramble, v);
+#pragma unroll
+        for (int j = 0; j < 8; j++) x[j] = v[j] / mean - (double)((v[j] > 0.0) - (v[j] < 0.0));
+#pragma unroll
+        for (int j = 0; j < 8; j++) { sum += x[j]; sumsq += x[j] * x[j]; }
+    }
+    {
+        double v[8], x[8];
+        wb_llr_stats_load8<FRAMING>(row, NB, scramble, v);
+#pragma unroll
+        for (int j = 0; j < TAIL; j++) x[j] = v[j] / mean - (double)((v[j] > 0.0) - (v[j] < 0.0));
+#pragma unroll
+        for (int j = 0; j < TAIL; j++) { sum += x[j]; sumsq += x[j] * x[j]; }
+    }
+    const double estvar = ((double)n * sumsq - sum * sum) / (double)(n * (n - 1));
+    return 4.0 * wb_esn0_from_var(estvar);
+}
+
 __global__ void __launch_bounds__(128)
 wb_llr_stats_kernel(const float *sd, unsigned long long sd_stride, const unsigned *jobs, double *c4,
                     const wb_cursor *cur, int job_cap, int n_streams, int framing, const uint8_t *scramble)
@@ -77,24 +137,8 @@ wb_llr_stats_kernel(const float *sd, unsigned long long sd_stride, const unsigne
     int s = g / job_cap, k = g - s * job_cap;
     if (s >= n_streams || k >= (int)cur[s].n_jobs) return;
     const float *row = sd + (size_t)s * sd_stride + jobs[(size_t)s * job_cap + k];
-    const int n = WB_NCODE;
-    double sum = 0.0, sumsq = 0.0, mean, estvar;
-    for (int c = 0; c < n; c++) {
-        double v = (double)row[wb_cw_symbol(framing, c)];    /* |.| : descrambling only flips the sign */
-        sum += fabs(v);
-    }
-    mean = sum / (double)n;
-    sum = 0.0;
-    for (int c = 0; c < n; c++) {
-        double v = (double)row[wb_cw_symbol(framing, c)];
-        if (framing == WB_FRAMING_V2 && scramble[c % WB_SCRAMBLE_LEN]) v = -v;
-        double sign = (double)((v > 0.0) - (v < 0.0));
-        double x = v / mean - sign;
-        sum += x;
-        sumsq += x * x;
-    }
-    estvar = ((double)n * sumsq - sum * sum) / (double)(n * (n - 1));
-    c4[(size_t)s * job_cap + k] = 4.0 * wb_esn0_from_var(estvar);
+    c4[(size_t)s * job_cap + k] = (framing == WB_FRAMING_V1) ? wb_llr_stats_row<WB_FRAMING_V1>(row, scramble)
+                                                             : wb_llr_stats_row<WB_FRAMING_V2>(row, scramble);
 }
 
 /* standalone sd_to_llr over n blocks of 2580 soft decisions (wb_sd_to_llr_batch): statistics */
@@ -103,6 +147,7 @@ wb_llr_stats_plain_kernel(const float *sd, double *c4, long long n_blocks)
 {
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_blocks) return;
+    /* the last block's tail load would read 4 floats past the array: the plain form takes it element by element */
     const float *row = sd + (size_t)g * WB_NCODE;
     const int n = WB_NCODE;
     double sum = 0.0, sumsq = 0.0, mean, estvar;

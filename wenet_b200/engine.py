@@ -100,6 +100,9 @@ ABI = [
     ("wb_launch_count", _U64, [_VP]),
     ("wb_last_codewords", _U64, [_VP]),
     ("wb_last_samples", _U64, [_VP]),
+    ("wb_copy_probe_create", C.c_int, [C.c_int, _SZ, C.POINTER(_VP)]),
+    ("wb_copy_probe_run", C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    ("wb_copy_probe_destroy", None, [_VP]),
     ("wb_host_alloc", _VP, [_SZ]),
     ("wb_host_free", None, [_VP]),
     ("wb_geometry", C.c_int, [_VP, _VP, C.c_int]),
@@ -151,6 +154,38 @@ class PinnedBuffer:
             self._lib.wb_host_free(p)
 
 
+class CopyProbe:
+    """Pinned host <-> device copy rate of one GPU (wb_copy_probe_*): the ceiling of the host-buffer (e2e) path.  Run on
+    every GPU of a box at the same time it gives the box's concurrent-copy ceiling (bench.py, tools/micro/pcie_multi.cu)."""
+
+    def __init__(self, device=0, nbytes=1 << 30):
+        self.lib = load_library()
+        self.nbytes = nbytes
+        self.h = _VP()
+        rc = self.lib.wb_copy_probe_create(device, nbytes, C.byref(self.h))
+        if rc != 0:
+            raise WbError(rc, self.lib.wb_last_error().decode())
+
+    def run(self, iters=4, d2h=False):
+        """-> GB/s of `iters` back-to-back copies of nbytes (CUDA events on the copy stream)"""
+        ms = C.c_float(0)
+        rc = self.lib.wb_copy_probe_run(self.h, iters, 1 if d2h else 0, C.byref(ms))
+        if rc != 0:
+            raise WbError(rc, self.lib.wb_last_error().decode())
+        return self.nbytes * iters / (ms.value * 1e-3) / 1e9
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.wb_copy_probe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Engine:
     """n_streams FSK demodulators + deframers + LDPC decoders resident on one GPU.
 
@@ -177,6 +212,7 @@ class Engine:
         self.h = _VP()
         self._check(self.lib.wb_create(C.byref(cfg), C.byref(self.h)))
         self.n_streams = n_streams
+        self.device = device
         self.keep_llr = keep_llr
         self.chunk_samples = chunk_samples
         g = np.zeros(14, dtype=np.int32)
