@@ -491,8 +491,7 @@ extern "C" int wb_create(const wb_config *cfg, wb_engine **out)
         int dev_smem_sm = 0, dev_smem_blk = 0;
         CRE(cudaDeviceGetAttribute(&dev_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cfg->device));
         CRE(cudaDeviceGetAttribute(&dev_smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
-        auto smem_for = [&](int spb) { return ((sizeof(wb_fsk_sc) * spb + 127) / 128) * 128 + (size_t)3 * (e->fp.Ndft / 4) * sizeof(float2) +
-                                              (size_t)spb * e->fp.sreg; };
+        auto smem_for = [&](int spb) { return (size_t)wb_geom_head(spb, (int)sizeof(wb_fsk_sc)) + (size_t)spb * e->fp.sreg; };
         int spb = 0;
         for (int ctas = 2; ctas >= 1 && spb == 0; ctas--)
             for (int t = max_spb; t >= (ctas == 2 ? 4 : 2); t--)      /* >= 2: the re and im fine-timing chains run in warps 0 and 1 */

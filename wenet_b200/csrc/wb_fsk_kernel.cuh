@@ -149,15 +149,32 @@ __device__ __forceinline__ float2 wb_ucmul(float2 a)
     return c;
 }
 
-/* cf32 frames go global -> shared memory with cp.async (no registers, no conversion) */
-__device__ __forceinline__ void wb_cp_async8(void *smem_dst, const void *gmem_src)
+/* cf32 frames go global -> shared memory as ONE TMA bulk copy per stream and frame (cp.async.bulk + an mbarrier that
+   counts the bytes): no registers, no conversion, one instruction where 13 cp.async per lane used to be.  Source and
+   destination must be 16-byte aligned and the size a multiple of 16, while a frame starts at any sample (8 bytes): the
+   copy starts one sample early when the row position is odd and the landing place in X is skewed by `dlt` in {0, 1}
+   samples, chosen per frame, so that both ends are aligned (see the kernel).  The .shared::cluster destination form is
+   used with the CTA's own shared-memory address (a CTA is its own cluster of one). */
+__device__ __forceinline__ unsigned wb_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void wb_mbar_init(void *bar, unsigned count)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
-                 : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wb_smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void wb_cp_async_wait()
+__device__ __forceinline__ void wb_tma_fetch(void *smem_dst, const void *gmem_src, unsigned bytes, void *bar)
 {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    /* what the lanes of this warp read from / wrote to the landing zone (generic proxy) comes before the copy's writes */
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wb_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(wb_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(wb_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void wb_mbar_wait(void *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(wb_smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
 }
 
 /* Tensor memory as lane-private scratch: this kernel issues no MMA, so its 256 KB per SM sit idle, while the register
@@ -326,7 +343,8 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     const int fmt = p.in_fmt;
 
     wb_fsk_sc *sc = reinterpret_cast<wb_fsk_sc *>(wb_fsk_raw);
-    float2 *TW = reinterpret_cast<float2 *>(wb_fsk_raw + ((sizeof(wb_fsk_sc) * spb + 127) / 128) * 128);
+    unsigned long long *MB = reinterpret_cast<unsigned long long *>(wb_fsk_raw + sizeof(wb_fsk_sc) * spb);   /* one mbarrier per stream */
+    float2 *TW = reinterpret_cast<float2 *>(wb_fsk_raw + wb_geom_head(spb, (int)sizeof(wb_fsk_sc)) - 3 * (Ndft >> 2) * 8);
     unsigned char *regions = reinterpret_cast<unsigned char *>(TW + 3 * (Ndft >> 2));
     float2 *X = reinterpret_cast<float2 *>(regions + (size_t)warp * sreg);
     float2 *Y = X + XLEN;
@@ -348,6 +366,13 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     for (int q = 0; q < WB_NEQ; q++) est[q] = 0.0f;
     /* (-DWB_NO_TMEM, the `san` build of the Makefile, keeps these values in registers instead: compute-sanitizer's
        synccheck mistakes tcgen05.alloc for an uninitialised mbarrier and stops the kernel) */
+    if (CF32 && lane == 0) {
+        wb_mbar_init(&MB[warp], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#ifdef WB_NO_TMEM
+    __syncthreads();
+#endif
 #ifndef WB_NO_TMEM
     /* 32 TMEM columns per CTA: 8 per warp, warps of one quadrant side by side */
     static_assert(WB_NEQ == 4, "est[4] + stash fill one 8-column TMEM row");
@@ -368,7 +393,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 #pragma unroll
         for (int q = 0; q < WB_NEQ; q++)
             if (lane + 32 * q < nh) est[q] = st->fft_est[lane + 32 * q];
-        if (lane < nst) X[lane] = st->samp_old[lane];
+        if (lane < nst) stash = st->samp_old[lane];
         if (lane == 0) {
             wb_fsk_sc &c = sc[warp];
             for (int m = 0; m < M; m++) { c.phi_c[m] = st->phi_c[m]; c.pb[m] = (short)st->fbin[m]; c.nb[m] = 0; }
@@ -380,25 +405,28 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
         for (int m = 0; m < M; m++) { c.phi_c[m] = make_float2(1.0f, 0.0f); c.pb[m] = 0; c.nb[m] = 0; }
         c.nin = (short)N_; c.flags = 0; c.norm = 0.0f; c.ppm = 0.0f; c.rx_timing = 0.0f; c.tcr = c.tci = 0.0f;
     }
-    /* cf32: start the copy of the frame at row position POS into X[nst ..] (zeros past the fill mark) */
-#define WB_FETCH_CF32(POS)                                                                              \
+    /* cf32: start the copy of the NIN-sample frame at row position POS; its first sample lands at X[nst + dlt], dlt =
+       (warp + nst + POS) & 1 (regions of odd warps start 8 bytes off a 16-byte boundary).  When POS is odd the copy
+       starts one sample early -- that sample falls on the newest old sample's slot, which phase A rewrites after the
+       landing -- and the byte count is rounded up to 16: at most X[XLEN + 1] = Y[1] is touched, which is why the FFT
+       work buffer starts at Y + 2. */
+#define WB_FETCH_CF32(POS, NIN)                                                                         \
     do {                                                                                                \
-        int sgv_ = sgc;                                                                                 \
-        asm volatile("" : "+r"(sgv_));                                                                  \
-        const float2 *row_ = reinterpret_cast<const float2 *>(WB_ROW_IN(sgv_)) + (POS);                 \
-        const int lim_ = (int)min((unsigned)NMAX, fill > (POS) ? fill - (POS) : 0u);                  \
-        float2 *xd_ = X + nst;                                                                          \
-        _Pragma("unroll")                                                                               \
-        for (int q_ = 0; q_ < NPRE; q_++) {                                                             \
-            const int n_ = lane + 32 * q_;                                                              \
-            if (n_ < lim_) wb_cp_async8(xd_ + n_, row_ + n_);                                           \
-            else if (n_ < NMAX) xd_[n_] = make_float2(0.0f, 0.0f);                                    \
+        if (lane == 0) {                                                                                \
+            int sgv_ = sgc;                                                                             \
+            asm volatile("" : "+r"(sgv_));                                                              \
+            const unsigned odd_ = (POS) & 1u;                                                           \
+            const float2 *src_ = reinterpret_cast<const float2 *>(WB_ROW_IN(sgv_)) + ((POS) - odd_);    \
+            float2 *dst_ = X + nst + ((warp + nst + (int)(POS)) & 1) - (int)odd_;                       \
+            wb_tma_fetch(dst_, src_, (((unsigned)(NIN) + odd_ + 1u) & ~1u) * 8u, &MB[warp]);            \
         }                                                                                               \
     } while (0)
 #ifndef WB_NO_TMEM
-    wb_tmem_st8(taddr, est[0], est[1], est[2], est[3], 0.0f, 0.0f, 0.0f, 0.0f);
+    wb_tmem_st8(taddr, est[0], est[1], est[2], est[3], stash.x, stash.y, 0.0f, 0.0f);
 #endif
-    if (CF32 && have) WB_FETCH_CF32(pos);
+    /* a frame is fetched if and only if it will be demodulated: the condition is the loop's `active` one pass ahead, so
+       every copy is waited for before the kernel ends and every wait has its copy */
+    if (CF32 && have && (pos + (unsigned)nin <= fill) && ((unsigned)NBITS <= a.sd_cap)) WB_FETCH_CF32(pos, nin);
 
     const float omt = __fsub_rn(1.0f, p.tc);
     constexpr bool blocked = BLK;          /* P == Ts: the configuration every Wenet script uses */
@@ -411,14 +439,15 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
         if (!__syncthreads_or(active)) break;
         WB_CLK(6);      /* C + loop barrier */
         const unsigned pos_next = pos + nin;
-        const int xo = nst - (NMEM - nin);         /* X index of the first mixer sample */
+        const int dlt = CF32 ? ((warp + nst + (int)pos) & 1) : 0;     /* this frame's samples start at X[nst + dlt] */
+        const int xo = nst - (NMEM - nin) + dlt;   /* X index of the first mixer sample */
 
         /* ================= A: stream warps ================= */
         if (active) {
 #ifndef WB_NO_TMEM
             {
-                float d0, d1, d2, d3;
-                wb_tmem_ld8(taddr, est[0], est[1], est[2], est[3], d0, d1, d2, d3);
+                float d2, d3;
+                wb_tmem_ld8(taddr, est[0], est[1], est[2], est[3], stash.x, stash.y, d2, d3);
             }
 #endif
             /* the leaf butterflies' table entries first: their latency hides behind the landing of the frame */
@@ -440,9 +469,9 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 }
             }
             if (CF32) {
-                /* this frame's samples were sent on their way (cp.async, global -> shared) at the end of the previous
-                   frame; wait for them */
-                wb_cp_async_wait();
+                /* this frame's samples were sent on their way (one TMA bulk copy, global -> shared) at the end of the
+                   previous frame; wait for them */
+                wb_mbar_wait(&MB[warp], (n_out / (unsigned)NBITS) & 1u);     /* the barrier's phase = frames so far, mod 2 */
             } else {
                 /* converted formats go through registers: L2 hits (each frame is prefetched into L2 a frame ahead) */
                 int sgv = sgc;
@@ -461,6 +490,9 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                     if (n < NMAX) X[nst + n] = wb_convert<false>(fmt, pre_lo[q], pre_hi[q]);
                 }
             }
+            /* the old samples the mixer reaches back to, right in front of the new ones (after the landing: a copy that
+               started one sample early has written over the newest of them) */
+            if (lane < nst) X[dlt + lane] = stash;
             {
                 /* the frame after this one -> L2: one 128-byte line per lane, no registers held */
                 int sgv = sgc;
@@ -475,7 +507,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             /* Estimator FFT (reference src/fsk.c:583-628, src/kiss_fft.c:238-306): decimation in time, the
                reference's butterfly order.  Leaf level fused with the window: leaf butterfly t combines the
                inputs perm[t*p] + d*Ndft/p, of which only those below nwin = nin - Ndft are non-zero. */
-            float2 *F = Y;
+            float2 *F = Y + 2;                       /* Y[0..1] can hold the tail of a skewed frame (see WB_FETCH_CF32) */
 #pragma unroll
             for (int b = 0; b < 2; b++) {
                 const int t = lane + 32 * b;
@@ -486,7 +518,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                         const int n = lbase[b] + dd * istr;
                         f[dd] = make_float2(0.0f, 0.0f);
                         if (dd < pp0 && n < nwin) {
-                            const float2 x = X[nst + n];
+                            const float2 x = X[nst + dlt + n];
                             f[dd].x = __fmul_rn(lh[b][dd], x.x); f[dd].y = __fmul_rn(lh[b][dd], x.y);
                         }
                     }
@@ -600,7 +632,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
             }
             /* the samples the next frame's mixer reaches back to (reference src/fsk.c:851 keeps 4 Ts, uses at most
                2 Ts + Ts/2) sit where the mixer products are about to land: lift them into registers */
-            if (lane < nst) stash = X[nin + lane];
+            if (lane < nst) stash = X[nin + dlt + lane];
 #ifndef WB_NO_TMEM
             wb_tmem_st8(taddr, est[0], est[1], est[2], est[3], stash.x, stash.y, 0.0f, 0.0f);
 #endif
@@ -609,7 +641,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 const bool first = c.pb[0] == 0;         /* fsk->f_est[0] < 1, reference src/fsk.c:729 */
 #pragma unroll
                 for (int m = 0; m < M; m++) { c.nb[m] = (short)freqi[m]; if (first) c.pb[m] = (short)freqi[m]; }
-                c.nin = (short)nin; c.flags = 1;
+                c.nin = (short)nin; c.flags = 1 | (dlt << 1);
             }
         } else if (lane == 0) {
             sc[warp].flags = 0;
@@ -643,8 +675,9 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 ph = wb_cmul2(__ldg(&p.back[nin_idx * nh + pb]), ph);     /* reference src/fsk.c:756-759 */
                 float2 d = __ldg(&p.dphi[pb]);
                 const float2 dnew = __ldg(&p.dphi[nbn]);
-                const float2 *src = Xs + (nst - nold);
-                float2 *dst = (m == 0) ? Xs + (nst - nold) : Xs + XLEN + (m - 1) * ylen;
+                const int sdl = (c.flags >> 1) & 1;            /* that stream's landing skew this frame */
+                const float2 *src = Xs + (nst - nold) + sdl;
+                float2 *dst = (m == 0) ? Xs + (nst - nold) + sdl : Xs + XLEN + (m - 1) * ylen;
                 const int nold_hi = 2 * TS + TS / 2;          /* >= every possible nold */
                 const int seg0 = p.b1_seg[warp], seg1 = p.b1_seg[warp + 1];
                 /* old -> new samples: comp_normalize + this frame's tone, reference src/fsk.c:787-788 */
@@ -1011,18 +1044,10 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 }
             }
             __syncwarp();
-            /* old samples for the next frame */
-#ifndef WB_NO_TMEM
-            {
-                float e0, e1, e2, e3, d2, d3;
-                wb_tmem_ld8(taddr, e0, e1, e2, e3, stash.x, stash.y, d2, d3);
-            }
-#endif
-            if (lane < nst) X[lane] = stash;
-            /* the integrator outputs in X are consumed: send the next frame's samples on their way */
-            if (CF32) {
+            /* the integrator outputs in X are consumed: send the next frame's samples on their way (if there is one) */
+            if (CF32 && (pos_next + (unsigned)nin_next <= fill) && (n_out + 2u * (unsigned)NBITS <= a.sd_cap)) {
                 const unsigned pn = pos_next;
-                WB_FETCH_CF32(pn);
+                WB_FETCH_CF32(pn, nin_next);
             }
             if (lane == 0) {
 #pragma unroll
@@ -1044,8 +1069,8 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     /* ---- write the state back ---- */
 #ifndef WB_NO_TMEM
     {
-        float d0, d1, d2, d3;
-        wb_tmem_ld8(taddr, est[0], est[1], est[2], est[3], d0, d1, d2, d3);
+        float d2, d3;
+        wb_tmem_ld8(taddr, est[0], est[1], est[2], est[3], stash.x, stash.y, d2, d3);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -1057,7 +1082,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 #pragma unroll
         for (int q = 0; q < WB_NEQ; q++)
             if (lane + 32 * q < nh) st->fft_est[lane + 32 * q] = est[q];
-        if (lane < nst) st->samp_old[lane] = X[lane];
+        if (lane < nst) st->samp_old[lane] = stash;
         if (n_out >= (unsigned)NBITS) {
             const float *lastf = WB_ROW_SD(sg) + n_out - NBITS;
             for (int i = lane; i < NBITS; i += 32) st->sd_last[i] = lastf[i];

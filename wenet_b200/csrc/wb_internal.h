@@ -53,13 +53,16 @@
 WB_HD constexpr int wb_geom_xlen(int Ts) { return ((2 * Ts + Ts / 2) + (Ts * WB_FRAME_SYMS + Ts / 2) + 1) & ~1; }
 WB_HD constexpr int wb_geom_ylen(int Ts, int step) { return ((Ts * WB_FRAME_SYMS + 2 * Ts - step) + 1) & ~1; }
 WB_HD constexpr int wb_geom_blen(int M, int ylen) { return (M - 1) * ylen > WB_MAX_NDFT ? (M - 1) * ylen : WB_MAX_NDFT; }
-WB_HD constexpr int wb_geom_efl(int P) { return (WB_FRAME_SYMS + 1) * P > 2 * ((WB_FRAME_SYMS + 2) / 2) * P ? (WB_FRAME_SYMS + 1) * P : 2 * ((WB_FRAME_SYMS + 2) / 2) * P; }
+WB_HD constexpr int wb_geom_efl(int P) { return (WB_FRAME_SYMS + 1) * P; }          /* one e_i per integrator output */
 WB_HD constexpr int wb_geom_sreg(int xlen, int blen, int efl)
 {
     const int bytes = (xlen + blen) * 8 + ((efl * 4 + 7) & ~7);
     const int sreg = (bytes & ~15) + 8;
     return sreg < bytes ? sreg + 16 : sreg;
 }
+/* bytes in front of the stream regions: the frame scalars (wb_fsk_sc, `sc_bytes` each), one 8-byte mbarrier per stream
+   (the TMA frame fetch), rounded to 128, then the FFT twiddles */
+WB_HD constexpr int wb_geom_head(int spb, int sc_bytes) { return ((sc_bytes + 8) * spb + 127) / 128 * 128 + 3 * (WB_MAX_NDFT / 4) * 8; }
 WB_HD constexpr int wb_blk_ylen(int Ts) { return wb_geom_ylen(Ts, 1); }
 WB_HD constexpr int wb_blk_blen(int M, int Ts) { return wb_geom_blen(M, wb_blk_ylen(Ts)); }
 WB_HD constexpr int wb_blk_sreg(int M, int Ts) { return wb_geom_sreg(wb_geom_xlen(Ts), wb_blk_blen(M, Ts), wb_geom_efl(Ts)); }
