@@ -700,6 +700,9 @@ def test_multi_engine_equals_one_engine(eng_mod, oracle_port):
     nsamp = min(r.size for r in raws) // 2
     ndev = _device_count()
     devices = list(range(ndev)) if ndev > 1 else [0, 0]
+    from wenet_b200.multi import probe_copy_rates
+    rates = probe_copy_rates(sorted(set(devices)), seconds=0.05, nbytes=8 << 20)
+    assert len(rates) == len(set(devices)) and all(r > 1.0 for r in rates)       # GB/s, pinned host -> device
     me = MultiEngine(n, devices=devices, weights=[1.0 + 0.5 * (i % 2) for i in range(len(devices))], in_fmt="cu8", framing="v1",
                      chunk_samples=nsamp + 1024)
     pb = me.pinned_block(nsamp)

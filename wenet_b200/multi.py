@@ -23,6 +23,35 @@ from . import engine as E
 from . import sharding
 
 
+def probe_copy_rates(devices, seconds=0.5, nbytes=256 << 20):
+    """Pinned-host -> device copy rate (GB/s) of every device in `devices` with ALL of them copying at once: what each
+    GPU can take when the whole box is busy feeding.  On an HGX box the GPUs do not get equal shares (shared host bridges,
+    profiles/r02_pcie_multi_8gpu.jsonl); MultiEngine(weights=probe_copy_rates(devs)) sizes the stream blocks accordingly."""
+    import threading
+    import time
+    devices = list(devices)
+    probes = [E.CopyProbe(d, nbytes) for d in devices]
+    rates = [0.0] * len(devices)
+    gate = threading.Barrier(len(devices))
+
+    def work(i):
+        p = probes[i]
+        p.run(1)
+        gate.wait()
+        t0, nb = time.perf_counter(), 0
+        while time.perf_counter() - t0 < seconds:
+            p.run(1)
+            nb += p.nbytes
+        rates[i] = nb / (time.perf_counter() - t0) / 1e9
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(devices))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for p in probes:
+        p.close()
+    return rates
+
+
 class MultiEngine:
     def __init__(self, n_streams, devices=(0,), weights=None, engines_per_device=1, engine_cls=None, **engine_kw):
         devices = list(devices)
