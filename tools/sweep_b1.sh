@@ -1,6 +1,5 @@
-set -e
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-for cfg in "8 0.82" "8 0.7" "8 0.9" "4 0.8" "14 0.85" "14 0.75" "1 0.8"; do
+# sweep of the mixer phase's redundancy (warps W sharing the oscillator chains, geometric segment ratio R): bench.py headline timing only
+for cfg in "4 0.7" "3 0.7" "5 0.7" "6 0.7" "4 0.6" "4 0.8" "5 0.8" "6 0.8" "5 0.6" "8 0.8"; do
   set -- $cfg
-  WB_FSK_B1W=$1 WB_FSK_B1R=$2 python bench.py --no-cpu-baseline --no-e2e --steps 3 --warmup 2 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$cfg', d['value'], d['roofline']['kernel_ms'])"
+  WB_FSK_B1W=$1 WB_FSK_B1R=$2 python bench.py --no-cpu-baseline --no-e2e --no-extra --no-parity --steps 4 --warmup 2 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('W R = $cfg', d['value'], d['roofline']['kernel_ms'])"
 done
