@@ -52,6 +52,31 @@ def test_x87_emulation(hm):
     a = _call(hm.wbh_llr_scale, c, sd, out_dtype=np.float32)
     b = _call(hm.wbh_llr_scale_x87, c, sd, out_dtype=np.float32)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    # the one-multiplication form the decoder uses (exact emulation only next to a float rounding midpoint)
+    f = _call(hm.wbh_llr_scale_fast, c, sd, out_dtype=np.float32)
+    assert np.array_equal(f.view(np.uint32), b.view(np.uint32))
+
+
+def test_llr_scale_fast_next_to_float_midpoints(hm):
+    """products engineered to land on, and within a few double ulps of, the midpoint between two floats -- where rounding
+    the exact product to 64 bits (the reference's x87 fmul) or to 53 bits first can decide the float differently -- and
+    where the 53-bit product is itself a tie: the fast form must agree with genuine long double arithmetic on all"""
+    rng = np.random.default_rng(7)
+    n = 400000
+    sd = (rng.standard_normal(n) * 10 ** rng.uniform(-3, 1, n)).astype(np.float32)
+    sd[sd == 0] = np.float32(1.0)
+    # target: a float midpoint t = (k + 0.5) ulp; c = t / sd rounded, then nudged by -3..3 double ulps
+    k = rng.integers(1 << 23, 1 << 24, n).astype(np.float64)
+    t = (k + 0.5) * 2.0 ** rng.integers(-30, 4, n)
+    c = np.abs(t / sd.astype(np.float64))
+    c = (c.view(np.uint64) + rng.integers(-3, 4, n).astype(np.uint64)).view(np.float64)
+    ref = _call(hm.wbh_llr_scale_x87, c, sd, out_dtype=np.float32)
+    got = _call(hm.wbh_llr_scale_fast, c, sd, out_dtype=np.float32)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # how many of them actually sat in the guarded window (the test is vacuous if none did)
+    p = c * sd.astype(np.float64)
+    low = p.view(np.uint64) & np.uint64(0x1fffffff)
+    assert np.count_nonzero((low >= 0x0fffffff) & (low <= 0x10000001)) > 1000
 
 
 def test_phi0_tables(hm, oracle_port):

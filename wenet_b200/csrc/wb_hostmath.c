@@ -26,6 +26,12 @@ void wbh_llr_scale(const double *c, const float *sd, float *out, long n)
     for (i = 0; i < n; i++) out[i] = wb_llr_scale(c[i], sd[i]);
 }
 
+void wbh_llr_scale_fast(const double *c, const float *sd, float *out, long n)
+{
+    long i;
+    for (i = 0; i < n; i++) out[i] = wb_llr_scale_fast(c[i], sd[i]);
+}
+
 /* the same expressions in genuine x87 long double, as gcc compiles the reference */
 void wbh_esn0_from_var_x87(const double *v, double *out, long n)
 {

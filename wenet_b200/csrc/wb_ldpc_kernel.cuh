@@ -171,7 +171,7 @@ wb_llr_scale_kernel(const float *sd, const double *c4, float *llr, long long n_b
 {
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_blocks * WB_NCODE) return;
-    llr[g] = wb_llr_scale(c4[g / WB_NCODE], sd[g]);
+    llr[g] = wb_llr_scale_fast(c4[g / WB_NCODE], sd[g]);
 }
 
 /* ---- K4 ------------------------------------------------------------------ */
@@ -182,6 +182,7 @@ struct wb_ldpc_smem {
     unsigned ballot[(WB_NCODE + 31) / 32 + 1];   /* hard decisions by slot, bit l of word w = slot 32w + l */
     unsigned nat[(WB_NCODE + 31) / 32 + 1];      /* ... and by variable, after the decode */
     unsigned crc_part[4];
+    unsigned nsat[2];                   /* satisfied checks of this / the next iteration (counted with one atomic per warp) */
 };
 
 /* phi0 (reference src/phi0.c:13-218): one 4-byte load; the few buckets with a breakpoint inside carry a flag and
@@ -249,7 +250,7 @@ wb_ldpc_kernel(wb_ldpc_args a, long long n_direct)
             if (c < WB_NCODE) {
                 float v = row[wb_cw_symbol(a.framing, c)];
                 if (a.framing == WB_FRAMING_V2 && a.scramble[c % WB_SCRAMBLE_LEN]) v = -v;
-                const float l = wb_llr_scale(c4, v);
+                const float l = wb_llr_scale_fast(c4, v);
                 sm.msg[c] = l;
                 if (a.llr_out) a.llr_out[slot * WB_NCODE + c] = l;
             }
@@ -281,12 +282,15 @@ wb_ldpc_kernel(wb_ldpc_args a, long long n_direct)
             }
         }
     }
+    if (tid < 2) sm.nsat[tid] = 0;
     __syncthreads();
 
     int result = a.max_iter, pcc = -1;
     for (int iter = 0; iter < a.max_iter; iter++) {
         /* ---- check-node pass, reference src/mpdecode_core.c:412-436 ---- */
-        int nsat = 0;
+        /* the two rounds touch disjoint checks: no barrier between them; the satisfied checks are counted with one
+           shared-memory atomic per warp and read after the variable pass (one CTA barrier less per iteration) */
+        int nsat_mine = 0;
 #pragma unroll 1
         for (int rnd = 0; rnd < 2; rnd++) {
             int j = tid + rnd * WB_LDPC_THREADS;
@@ -312,8 +316,14 @@ wb_ldpc_kernel(wb_ldpc_args a, long long n_direct)
                     sm.msg[t * WB_NPAR + j] = wb_signed(v, sign ^ (__float_as_uint(q[t]) >> 31));
                 }
             }
-            nsat += __syncthreads_count(sat);
+            nsat_mine += sat;
         }
+        {
+            const unsigned wsum = __reduce_add_sync(0xffffffffu, (unsigned)nsat_mine);
+            if (lane == 0 && wsum) atomicAdd(&sm.nsat[iter & 1], wsum);
+        }
+        __syncthreads();
+        if (tid == 0) sm.nsat[(iter + 1) & 1] = 0;      /* everyone read it before the barrier above; next used after the next one */
         /* ---- variable-node pass, reference src/mpdecode_core.c:439-464 ---- */
         int nz = 0;
 #pragma unroll
@@ -352,6 +362,7 @@ wb_ldpc_kernel(wb_ldpc_args a, long long n_direct)
             if (lane == 0 && w * 32 < WB_NCODE + 31) sm.ballot[w] = b;
         }
         nz = __syncthreads_or(nz);
+        const int nsat = (int)sm.nsat[iter & 1];
         /* exits, reference src/mpdecode_core.c:467-483 (data[] is all zero in run_ldpc_decoder) */
         if (!nz) { result = iter + 1; break; }
         pcc = nsat;

@@ -360,6 +360,20 @@ WB_HD float wb_llr_scale(double four_esn0, float sd)
     }
 }
 
+/* The same value from ONE double multiplication wherever that is provably enough.  The reference rounds the exact
+   77-bit product first to 64 bits (x87 fmul) and then to float; p = RN53(exact) rounded to float gives the same float
+   unless a float rounding midpoint lies within one double ulp of the exact product -- then and only then the low 29 bits
+   of p's significand are 2^28 - 1, 2^28 or 2^28 + 1 -- and those cases (3 in 2^29) take the exact 64-bit emulation.
+   Zeros, subnormals, infinities, NaNs and results outside the normal float range are the plain double product in
+   wb_llr_scale too.  (The decoder's prologue spent 8 % of the kernel's instructions in the emulation.) */
+WB_HD float wb_llr_scale_fast(double four_esn0, float sd)
+{
+    const double p = four_esn0 * (double)sd;
+    const uint32_t low = (uint32_t)wb_d2u(p) & 0x1fffffffu;
+    if (low - 0x0fffffffu <= 2u) return wb_llr_scale(four_esn0, sd);
+    return (float)p;
+}
+
 /* reciprocals that replace two double divisions of the frame-scalar chain (exhaustively checked over every float
    the divisions can see: wbh_check_div_2pi / wbh_check_div_48 in wb_hostmath.c) */
 #define WB_INV_2PI 0.15915494309189535      /* the double nearest to 1 / 6.283185307179586 */
