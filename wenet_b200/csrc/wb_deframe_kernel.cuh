@@ -9,7 +9,7 @@
  *     not cleared afterwards, so matching resumes over the stream with the packet excised;
  *   - the symbol that completes the UW is not part of the packet.
  *
- * One warp per stream.  While looking, 32 symbols are examined per step (fetched 128 at a time): a ballot gives the 32 new
+ * One warp per stream.  While looking, 32 symbols are examined per step (fetched 32 x WB_DEFRAME_NF at a time): a ballot gives the 32 new
  * hard bits, lane j forms the window as it stands after symbol j and scores it with one popcount;
  * the first hit (lowest lane) wins.  While collecting, nothing is touched: the packet is recorded
  * as an offset into the row and the scan jumps over it.  Packets are only located here; the symbols
@@ -19,6 +19,10 @@
 #define WB_DEFRAME_KERNEL_CUH
 
 #include "wb_internal.h"
+
+#ifndef WB_DEFRAME_NF
+#define WB_DEFRAME_NF 12
+#endif
 
 __global__ void __launch_bounds__(128)
 wb_deframe_kernel(wb_deframe_params p, wb_stream_state *state, wb_cursor *cursor, const float *sd,
@@ -46,18 +50,18 @@ wb_deframe_kernel(wb_deframe_params p, wb_stream_state *state, wb_cursor *cursor
             ind += n_new; t = n_new;
         }
     }
-    /* 128 symbols are fetched per round (four independent loads per lane in flight: the scan is a chain of
-       L2 round trips otherwise), then examined 32 at a time; a hit restarts the round at the jump target */
+    /* WB_DEFRAME_NF x 32 symbols are fetched per round (that many independent loads per lane in flight: the scan is a
+       chain of L2 round trips otherwise), then examined 32 at a time; a hit restarts the round at the jump target */
     while (t < n_new) {
-        float v4[4];
+        float v4[WB_DEFRAME_NF];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < WB_DEFRAME_NF; k++) {
             const int idx = t + 32 * k + lane;
             v4[k] = (idx < n_new) ? row[WB_CARRY_CAP + idx] : 0.0f;
         }
         bool jumped = false;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < WB_DEFRAME_NF; k++) {
             if (jumped || t >= n_new) break;
             const int idx = t + lane;
             const bool valid = idx < n_new;
