@@ -514,7 +514,9 @@ def main():
     port = None
     if not args.no_parity:
         from oracle import oracle as O           # the checker (test infrastructure): never inside a timed region
-        O.build()
+        if rank == 0:
+            O.build()                            # (one rank compiles it if the copy on this box looks stale; the others wait)
+        R.barrier()
         port = O.Oracle("port")
     parity = {"oracle": "CPU restatement oracle/liboracle.so (pinned against the compiled reference, tests/test_oracle_vs_ref.py)"} \
         if port else {"skipped": True}
@@ -768,6 +770,8 @@ def main():
     ladder_gpu = None
     if not args.no_e2e:
         rates = measure_ceiling()
+        if os.environ.get("WB_BENCH_SKEW_RATES"):          # test hook: pretend the ranks reach unequal rates (exercises the weighted path on any box)
+            rates = [r * (1.0 - 0.3 * (i % 2)) for i, r in enumerate(rates)]
         ceiling = sum(rates)
         # placement of the job's n x world streams over the ranks: equal blocks, or -- when the GPUs of the box do not reach
         # the same host -> device rate with all of them copying (HGX: GPUs behind a busier host bridge) -- blocks in
