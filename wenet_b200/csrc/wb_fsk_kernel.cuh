@@ -118,6 +118,23 @@ __device__ __forceinline__ void wb_mul2(unsigned long long a, unsigned long long
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
 }
+/* (a.x + b.x, a.y + b.y) as one packed addition: the same two IEEE sums */
+__device__ __forceinline__ float2 wb_add2p(float2 a, float2 b)
+{
+    unsigned long long r;
+    float2 c;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(wb_pack2(a.x, a.y)), "l"(wb_pack2(b.x, b.y)));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(r));
+    return c;
+}
+__device__ __forceinline__ float2 wb_sub2p(float2 a, float2 b)
+{
+    unsigned long long r;
+    float2 c;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(wb_pack2(a.x, a.y)), "l"(wb_pack2(b.x, b.y)));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(r));
+    return c;
+}
 /* a * b, reference src/comp_prim.h cmult: (a.x b.x - a.y b.y, a.x b.y + a.y b.x) */
 __device__ __forceinline__ float2 wb_cmul2p(float2 a, float2 b)
 {
@@ -587,15 +604,16 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                     const int base = ((t >> sh) << (sh + 2)) + k;
                     const int i0 = wb_fidx(base), i1 = wb_fidx(base + mm), i2 = wb_fidx(base + 2 * mm), i3 = wb_fidx(base + 3 * mm);
                     const float2 f0 = F[i0], f1 = F[i1], f2 = F[i2], f3 = F[i3];
-                    const float2 s0 = wb_cmul2(f1, w1);
-                    const float2 s1 = wb_cmul2(f2, w2);
-                    const float2 s2 = wb_cmul2(f3, w3);
-                    const float2 s5 = make_float2(__fsub_rn(f0.x, s1.x), __fsub_rn(f0.y, s1.y));
-                    const float2 aa = make_float2(__fadd_rn(f0.x, s1.x), __fadd_rn(f0.y, s1.y));
-                    const float2 s3 = make_float2(__fadd_rn(s0.x, s2.x), __fadd_rn(s0.y, s2.y));
-                    const float2 s4 = make_float2(__fsub_rn(s0.x, s2.x), __fsub_rn(s0.y, s2.y));
-                    F[i2] = make_float2(__fsub_rn(aa.x, s3.x), __fsub_rn(aa.y, s3.y));
-                    F[i0] = make_float2(__fadd_rn(aa.x, s3.x), __fadd_rn(aa.y, s3.y));
+                    /* (packed products and sums, reference src/kiss_fft.c:44-90: the same floats in fewer instructions) */
+                    const float2 s0 = wb_cmul2p(f1, w1);
+                    const float2 s1 = wb_cmul2p(f2, w2);
+                    const float2 s2 = wb_cmul2p(f3, w3);
+                    const float2 s5 = wb_sub2p(f0, s1);
+                    const float2 aa = wb_add2p(f0, s1);
+                    const float2 s3 = wb_add2p(s0, s2);
+                    const float2 s4 = wb_sub2p(s0, s2);
+                    F[i2] = wb_sub2p(aa, s3);
+                    F[i0] = wb_add2p(aa, s3);
                     F[i1] = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));
                     F[i3] = make_float2(__fsub_rn(s5.x, s4.y), __fadd_rn(s5.y, s4.x));
                 }
@@ -613,14 +631,14 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 do {                                                                                  \
                     const int k_ = (K);                                                               \
                     const float2 f0 = F[wb_fidx(k_)], f1 = F[wb_fidx(k_ + mtop)], f2 = F[wb_fidx(k_ + 2 * mtop)], f3 = F[wb_fidx(k_ + 3 * mtop)]; \
-                    const float2 s0 = wb_cmul2(f1, TW[k_]);                                           \
-                    const float2 s1 = wb_cmul2(f2, TW[2 * k_]);                                       \
-                    const float2 s2 = wb_cmul2(f3, TW[3 * k_]);                                       \
-                    const float2 s5 = make_float2(__fsub_rn(f0.x, s1.x), __fsub_rn(f0.y, s1.y));     \
-                    const float2 aa = make_float2(__fadd_rn(f0.x, s1.x), __fadd_rn(f0.y, s1.y));     \
-                    const float2 s3 = make_float2(__fadd_rn(s0.x, s2.x), __fadd_rn(s0.y, s2.y));     \
-                    const float2 s4 = make_float2(__fsub_rn(s0.x, s2.x), __fsub_rn(s0.y, s2.y));     \
-                    const float2 o0 = make_float2(__fadd_rn(aa.x, s3.x), __fadd_rn(aa.y, s3.y));     \
+                    const float2 s0 = wb_cmul2p(f1, TW[k_]);                                          \
+                    const float2 s1 = wb_cmul2p(f2, TW[2 * k_]);                                      \
+                    const float2 s2 = wb_cmul2p(f3, TW[3 * k_]);                                      \
+                    const float2 s5 = wb_sub2p(f0, s1);                                               \
+                    const float2 aa = wb_add2p(f0, s1);                                               \
+                    const float2 s3 = wb_add2p(s0, s2);                                               \
+                    const float2 s4 = wb_sub2p(s0, s2);                                               \
+                    const float2 o0 = wb_add2p(aa, s3);                                               \
                     const float2 o1 = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));     \
                     float pw0 = __fadd_rn(__fmul_rn(o0.x, o0.x), __fmul_rn(o0.y, o0.y));              \
                     float pw1 = __fadd_rn(__fmul_rn(o1.x, o1.x), __fmul_rn(o1.y, o1.y));              \
@@ -831,21 +849,23 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                     __syncwarp();
                     if (valid) {
                         const int k0 = SWZ ? ((u >> 1) & 7) : 0;
-                        float qr = 0.0f, qi = 0.0f;
+                        /* (real and imaginary sums side by side in packed additions: the same floats, half the instructions) */
+                        float2 q = make_float2(0.0f, 0.0f);
 #pragma unroll
                         for (int t = 0; t < TS; t++) {
-                            float sr, si;
+                            float2 sacc;
                             int o0;
-                            if (t == 0) { sr = vv[0].x; si = vv[0].y; o0 = 1; }
+                            if (t == 0) { sacc = vv[0]; o0 = 1; }
                             else {
-                                if (t == 1) { qr = vv[TS].x; qi = vv[TS].y; }
-                                else { qr = __fadd_rn(qr, vv[TS + t - 1].x); qi = __fadd_rn(qi, vv[TS + t - 1].y); }
-                                sr = qr; si = qi; o0 = t;
+                                if (t == 1) q = vv[TS];
+                                else q = wb_add2p(q, vv[TS + t - 1]);
+                                sacc = q; o0 = t;
                             }
 #pragma unroll
                             for (int o = 0; o < TS; o++)
-                                if (o >= o0) { sr = __fadd_rn(sr, vv[o].x); si = __fadd_rn(si, vv[o].y); }
-                            P[TS * u + (t ^ k0)] = make_float2(sr, si);
+                                if (o >= o0) sacc = wb_add2p(sacc, vv[o]);
+                            P[TS * u + (t ^ k0)] = sacc;
+                            const float sr = sacc.x, si = sacc.y;
                             const float pw = __fadd_rn(__fmul_rn(sr, sr), __fmul_rn(si, si));
                             e[t] = (m == 0) ? pw : __fadd_rn(e[t], pw);      /* reference src/fsk.c:864-867 */
                         }
