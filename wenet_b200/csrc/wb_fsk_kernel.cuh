@@ -779,7 +779,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                         WB_B1_STEP(j);
                     }
 #pragma unroll
-                    for (int j = 0; j < 8; j++) dst[n0 + (j ^ kb)] = xv[j];
+                    for (int j = 0; j < 8; j++) dst[(n0 ^ kb) ^ j] = xv[j];          /* n0 is a multiple of 8: n0 + (j ^ kb) */
                 }
                 /* (b) full batches, branch-free */
 #pragma unroll 1
@@ -792,7 +792,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 #pragma unroll
                     for (int j = 0; j < 8; j++) WB_B1_STEP(j);
 #pragma unroll
-                    for (int j = 0; j < 8; j++) dst[n0 + (j ^ kb)] = xv[j];
+                    for (int j = 0; j < 8; j++) dst[(n0 ^ kb) ^ j] = xv[j];          /* n0 is a multiple of 8: n0 + (j ^ kb) */
                 }
                 /* (c) a partial batch only ends the last segment (its swizzle key is 0) */
                 {
@@ -840,11 +840,13 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                     float2 *P = (m == 0) ? X + xo : Y + (m - 1) * ylen;
                     float2 vv[2 * TS - 1];
                     if (valid) {
+                        /* swizzled index 8 u + (o ^ k) = (8 u ^ k) ^ o for Ts = 8: one XOR with an immediate per access */
                         const int k0 = SWZ ? ((u >> 1) & 7) : 0, k1 = SWZ ? (((u + 1) >> 1) & 7) : 0;
+                        const int b0 = (TS * u) ^ k0, b1 = (TS * (u + 1)) ^ k1;
 #pragma unroll
-                        for (int o = 0; o < TS; o++) vv[o] = P[TS * u + (o ^ k0)];
+                        for (int o = 0; o < TS; o++) vv[o] = SWZ ? P[b0 ^ o] : P[TS * u + o];
 #pragma unroll
-                        for (int o = 0; o < TS - 1; o++) vv[TS + o] = P[TS * (u + 1) + (o ^ k1)];
+                        for (int o = 0; o < TS - 1; o++) vv[TS + o] = SWZ ? P[b1 ^ o] : P[TS * (u + 1) + o];
                     }
                     __syncwarp();
                     if (valid) {
@@ -864,7 +866,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 #pragma unroll
                             for (int o = 0; o < TS; o++)
                                 if (o >= o0) sacc = wb_add2p(sacc, vv[o]);
-                            P[TS * u + (t ^ k0)] = sacc;
+                            if (SWZ) P[((TS * u) ^ k0) ^ t] = sacc; else P[TS * u + t] = sacc;
                             const float sr = sacc.x, si = sacc.y;
                             const float pw = __fadd_rn(__fmul_rn(sr, sr), __fmul_rn(si, si));
                             e[t] = (m == 0) ? pw : __fadd_rn(e[t], pw);      /* reference src/fsk.c:864-867 */
