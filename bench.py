@@ -447,6 +447,119 @@ def bench_fsk_only(E, R, local, sources, n, chunk, M, warmup, steps):
         eng.close()
 
 
+def run_multiengine(args):
+    """`python bench.py --gpus N` WITHOUT torchrun: the same workload through wenet_b200.MultiEngine -- one process, one
+    engine pair and one feeder thread per GPU, no torch, no collective ("one host thread/process per GPU; outputs
+    gathered on the host").  Prints the same JSON line; `value` = input resident in HBM (every GPU's 4096 cf32 streams),
+    `e2e` = cu8 host buffers through MultiEngine.stream_step."""
+    from wenet_b200 import engine as E
+    from wenet_b200.multi import MultiEngine, probe_copy_rates
+    G, n, chunk = args.gpus, args.streams, args.chunk
+    total, n_src = n * G, min(args.sources, args.streams)
+    sources = make_sources(n_src, chunk, seed_base=0, mode="v1")
+    peaks = load_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    port = None
+    if not args.no_parity:
+        from oracle import oracle as O
+        O.build()
+        port = O.Oracle("port")
+    parity = {"oracle": "CPU restatement oracle/liboracle.so"} if port else {"skipped": True}
+    ok_all = True
+
+    # ---- value: every GPU's streams resident in HBM, one thread per GPU queues the steps ----
+    res = MultiEngine(total, devices=range(G), in_fmt="cf32", framing="v1", chunk_samples=chunk)
+
+    def setup(k, g):
+        g.feed(sources[:min(n_src, g.n_streams)] + [None] * (g.n_streams - min(n_src, g.n_streams)))
+        g.sync()
+        g.dev_replicate(min(n_src, g.n_streams), chunk, 4096 + 16 * 37)
+        g.dev_set_fill(chunk)
+    res.each(setup)
+
+    def steps(k, g, cnt, timed):
+        if timed:
+            g.timer_start()
+        for _ in range(cnt):
+            g.dev_set_fill(chunk)
+            g.process()
+        return g.timer_stop() if timed else g.sync()
+    clocks = ClockSampler(0)
+    res.each(lambda k, g: steps(k, g, max(args.warmup, 1), False))
+    l0 = res.launch_count
+    t0 = time.perf_counter()
+    ms = max(res.each(lambda k, g: steps(k, g, args.steps, True)))
+    t1 = time.perf_counter()
+    l1 = res.launch_count
+    clk = clocks.summary(t0, t1)
+    clocks.stop()
+    samples_step = res.last_samples
+    kms = np.max(np.stack(res.each(lambda k, g: g.last_kernel_ms().astype(np.float64))), axis=0)
+    value = samples_step * args.steps / (ms * 1e-3) / 1e6
+    fsk_gbs = ALG_BYTES_PER_SAMPLE_FSK * (samples_step / G) / (kms[0] * 1e-3) / 1e9
+    res.close()
+
+    # ---- e2e: cu8 host buffers, streams placed by the measured concurrent copy rates ----
+    ec = min(chunk, args.e2e_bytes // 2)
+    rates = probe_copy_rates(range(G), seconds=1.0)
+    weighted = min(rates) < 0.9 * max(rates)
+    me = MultiEngine(total, devices=range(G), weights=rates if weighted else None, engines_per_device=2, in_fmt="cu8",
+                     framing="v1", chunk_samples=ec + 1024)
+    pb = me.pinned_block(ec)
+    for s_ in range(total):
+        src = sources[s_ % n_src]
+        r = ((s_ // n_src) * 4688) % (chunk - ec) if chunk > ec else 0
+        pb.array[s_, :] = to_cu8(src[2 * r:2 * r + 2 * ec])
+    if port is not None:
+        me.step(pb.array)
+        me.sync()
+        rows = check_rows(total, n_src)
+        sd_ok = pk_ok = True
+        for s_ in rows:
+            sd_o, ref = oracle_decode(port, pb.array[s_], "cu8")
+            sd_g = me.drain_soft(s_)
+            sd_ok &= sd_g.size == sd_o.size and bool(np.array_equal(sd_g.view(np.uint32), sd_o.view(np.uint32)))
+            pk_ok &= me.drain_packets(s_) == ref["packets"]
+        me.drain_all_packets()
+        parity.update(e2e_streams_checked=len(rows), rows=rows, e2e_sd_equal=bool(sd_ok), e2e_packets_equal=bool(pk_ok))
+        ok_all &= sd_ok and pk_ok
+    for _ in range(max(args.warmup, 1)):
+        me.stream_step(pb.array)
+    me.flush()
+    npk = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        npk += len(me.stream_step(pb.array))
+    npk += len(me.flush())
+    dt = time.perf_counter() - t0
+    consumed = me.last_samples * args.steps
+    h2d = total * ec * 2
+    e2e = {"value": round(consumed / dt / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(npk // args.steps * 264), "ms_per_step": round(1e3 * dt / args.steps, 3), "in_fmt": "cu8",
+           "chunk_samples": ec, "engines": 2 * G, "crc_valid_packets_per_step": npk // args.steps,
+           "h2d_gbs": round(h2d * args.steps / dt / 1e9, 2), "h2d_rate_per_gpu_gbs": [round(x, 1) for x in rates],
+           "h2d_ceiling_gbs": round(sum(rates), 1), "frac_of_ceiling": round(h2d * args.steps / dt / 1e9 / sum(rates), 4),
+           "placement": "rate-weighted (MultiEngine weights = probe_copy_rates)" if weighted else "equal blocks",
+           "streams_per_engine": [b - a for a, b in me.ranges],
+           "api": "MultiEngine.stream_step(pinned host block) + flush: wb_feed_strided + wb_process + wb_sync + wb_drain_all_packets per engine thread"}
+    me.close()
+    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": G, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(args, G), parallelism="wenet_b200.MultiEngine: one process, one feeder thread per GPU, "
+                                                                 "no torch, no collective"),
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(l1 - l0), "parity": parity,
+            "roofline": {"bound": "hbm", "kernel": "wb_fsk_kernel", "achieved": round(fsk_gbs, 2), "peak": peak, "unit": "GB/s",
+                         "frac": round(fsk_gbs / peak, 4), "traffic": None,
+                         "kernel_ms": {"fsk": round(float(kms[0]), 3), "deframe": round(float(kms[1]), 3),
+                                       "llr_stats": round(float(kms[2]), 3), "ldpc": round(float(kms[3]), 3)}},
+            "cpu_baseline": None}
+    if not ok_all:
+        line.update(value=None, e2e=None, error="parity gate failed: see `parity`")
+    print(json.dumps(line), flush=True)
+    return 0 if ok_all else 1
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -480,6 +593,9 @@ def main():
     if args.impl == "reference":
         reference_arm(args, rank, world)
         return 0
+
+    if world == 1 and args.gpus > 1 and args.mode == "v1":
+        return run_multiengine(args)             # N GPUs from one process: the MultiEngine host object (no torchrun, no torch)
 
     R = Ranks(world, local)
     from wenet_b200 import engine as E          # raises if libwenet_b200.so is missing: no CPU fallback

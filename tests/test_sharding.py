@@ -155,6 +155,14 @@ def test_multi_engine_places_feeds_and_gathers():
     assert [me.owner(s) for s in (0, 3, 4, 8, 10)] == [(0, 0), (0, 3), (1, 0), (2, 0), (2, 2)]
     assert me.drain_soft(9)[0] == 109.0 and me.nin().size == n
     assert me.last_samples == 30 and me.launch_count == 15
+    # the pipelined form: packets of step k come back with step k + 1 (or with flush)
+    first = me.stream_step(block)
+    assert len(first) == 0
+    second = me.stream_step(block)
+    assert second["stream"].tolist() == list(range(n)) and set(second["seq"].tolist()) == {1}
+    last = me.flush()
+    assert last["stream"].tolist() == list(range(n)) and set(last["seq"].tolist()) == {2} and len(me.flush()) == 0
+    assert me.each(lambda k, g: g.n_streams) == [4, 4, 3]
     me.close()
     # weighted, two engines per device
     me = MultiEngine(12, devices=[0, 1], weights=[1.0, 2.0], engines_per_device=2, engine_cls=_FakeEngine)

@@ -89,6 +89,10 @@ class MultiEngine:
         futs = [self.pool.submit(fn, k, g) for k, g in enumerate(self.engines)]
         return [f.result() for f in futs]           # re-raises the first engine error
 
+    def each(self, fn):
+        """run fn(engine index, engine) on every engine, each in its own thread -> list of results"""
+        return self._each(fn)
+
     def pinned_block(self, nsamp):
         """one pinned host array [n_streams, elems * nsamp] for feed_strided (each engine copies its own rows of it)"""
         return E.PinnedBuffer((self.n_streams, E.FMT_ELEMS[self.fmt] * nsamp), E.FMT_DTYPE[self.fmt])
@@ -118,6 +122,53 @@ class MultiEngine:
             g.feed_strided(block[self.ranges[k][0]:self.ranges[k][1]])
             g.process()
         self._each(one)
+
+    def stream_step(self, block):
+        """The steady-state form of a receiver: on every engine (its own thread) collect the packets of the step queued
+        before (sync + drain), then feed this block and start processing it -- so one engine's host work and copy overlap
+        the kernels of the others, and with engines_per_device > 1 also those of its neighbour on the same GPU.
+        -> packets of the PREVIOUS step (global stream numbers), empty on the first call; flush() returns the last ones."""
+        def one(k):
+            g = self.engines[k]
+            out = None
+            if self._pending[k]:
+                g.sync()
+                out = g.drain_all_packets()
+                out["stream"] += self.ranges[k][0]
+            g.feed_strided(block[self.ranges[k][0]:self.ranges[k][1]])
+            g.process()
+            self._pending[k] = True
+            return out
+
+        def device(ks):
+            # the engines of ONE GPU take their turns in one thread: while engine i waits for its kernels and drains,
+            # the copy engine i + 1 queued a moment ago is running, and the other way round
+            return [one(k) for k in ks]
+        if not hasattr(self, "_pending"):
+            self._pending = [False] * len(self.engines)
+        groups = {}
+        for k, d in enumerate(self.devices):
+            groups.setdefault(d, []).append(k)
+        futs = [self.pool.submit(device, ks) for ks in groups.values()]
+        parts = [p for f in futs for p in f.result() if p is not None]
+        return np.concatenate(parts) if parts else np.zeros(0, dtype=self._pk_dtype())
+
+    def flush(self):
+        """wait for what stream_step queued last and return its packets"""
+        def one(k, g):
+            if not getattr(self, "_pending", [False] * len(self.engines))[k]:
+                return None
+            g.sync()
+            out = g.drain_all_packets()
+            out["stream"] += self.ranges[k][0]
+            self._pending[k] = False
+            return out
+        parts = [p for p in self._each(one) if p is not None]
+        return np.concatenate(parts) if parts else np.zeros(0, dtype=self._pk_dtype())
+
+    @staticmethod
+    def _pk_dtype():
+        return np.dtype([("stream", "<i4"), ("seq", "<u4"), ("payload", "u1", (E.PACKET_BYTES,))])
 
     def drain_all_packets(self):
         """-> (stream, seq, payload[256]) of every engine, global stream numbers, sorted by (stream, seq)"""
