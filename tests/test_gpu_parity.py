@@ -725,4 +725,15 @@ def test_multi_engine_equals_one_engine(eng_mod, oracle_port):
         want = oracle_port.deframer("v1", 10).feed(sd_o)["packets"]
         assert pk["payload"][pk["stream"] == s].tobytes() == want, s
     one.close()
+    # the pipelined receiver form: two more blocks through stream_step / flush, packets arrive one call later and carry on
+    # the per-stream codeword numbering
+    before = {s_: int(pk["seq"][pk["stream"] == s_].max()) for s_ in set(pk["stream"].tolist())}
+    assert len(me.stream_step(pb.array)) == 0
+    a = me.stream_step(pb.array)
+    b = me.flush()
+    assert len(a) and len(b) and len(me.flush()) == 0
+    for part in (a, b):
+        assert set(part["stream"].tolist()) <= set(range(n))
+    for s_, last in before.items():
+        assert a["seq"][a["stream"] == s_].min() > last and b["seq"][b["stream"] == s_].min() > a["seq"][a["stream"] == s_].max()
     me.close()
