@@ -756,6 +756,11 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                         ph = wb_cmul2p(ph, d);
                     }
 #pragma unroll 1
+                    for (; n + 32 <= seg0; n += 32) {        /* long bodies: the loop's back edge costs the chain a bubble */
+#pragma unroll
+                        for (int j = 0; j < 32; j++) ph = wb_cmul2p(ph, d);
+                    }
+#pragma unroll 1
                     for (; n + 8 <= seg0; n += 8) {
 #pragma unroll
                         for (int j = 0; j < 8; j++) ph = wb_cmul2p(ph, d);

@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwenet_b200.so")
+# (WB_LIBRARY: another build of the same library, e.g. an experiment beside the shipped one for an A/B timing on one box)
+LIB_PATH = os.environ.get("WB_LIBRARY") or os.path.join(_HERE, "libwenet_b200.so")
 
 FMT = {"cf32": 0, "cu8": 1, "cs16": 2, "s16": 3}
 FMT_DTYPE = {"cf32": np.float32, "cu8": np.uint8, "cs16": np.int16, "s16": np.int16}
