@@ -749,11 +749,30 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 /* (0) bare recurrence up to the segment start */
                 int n = 0;
                 {
+                    /* the switch sits at step 2 Ts - Ts/2, 2 Ts or 2 Ts + Ts/2 (nin = N + Ts/2, N, N - Ts/2): straight runs
+                       between those three points instead of a compare and a branch on every one of the first steps */
                     const int na = min(seg0, nold_hi + 1);
+                    if (na == nold_hi + 1) {
+                        constexpr int S0 = 2 * TS - TS / 2, HS = TS / 2;
+#pragma unroll
+                        for (int j = 0; j < S0; j++) ph = wb_cmul2p(ph, d);
+#pragma unroll
+                        for (int g = 0; g < 3; g++) {
+                            if (S0 + g * HS == nold) WB_B1_SWITCH();
+                            if (g < 2) {
+#pragma unroll
+                                for (int j = 0; j < HS; j++) ph = wb_cmul2p(ph, d);
+                            } else {
+                                ph = wb_cmul2p(ph, d);         /* step nold_hi itself */
+                            }
+                        }
+                        n = na;
+                    } else {
 #pragma unroll 1
-                    for (; n < na; n++) {
-                        if (n == nold) WB_B1_SWITCH();
-                        ph = wb_cmul2p(ph, d);
+                        for (; n < na; n++) {
+                            if (n == nold) WB_B1_SWITCH();
+                            ph = wb_cmul2p(ph, d);
+                        }
                     }
 #pragma unroll 1
                     for (; n + 32 <= seg0; n += 32) {        /* long bodies: the loop's back edge costs the chain a bubble */
