@@ -1472,11 +1472,12 @@ extern "C" int wb_tx_read_bits(wb_engine *e, int stream, uint8_t *bits, size_t c
 }
 
 #ifdef WB_PHASE_CLK
-/* debug build only (make dbg -> libwenet_b200_dbg.so): read and clear the per-phase cycle counters of wb_fsk_kernel */
-extern "C" int wb_debug_phase_clk(unsigned long long *out8)
+/* debug build only (make dbg -> libwenet_b200_dbg.so): read and clear the twelve cycle counters of wb_fsk_kernel
+   (0-3, 6: phases; 4, 5, 7: the last oscillator warp's way to its segment; 8-11: when each oscillator warp is done) */
+extern "C" int wb_debug_phase_clk(unsigned long long *out12)
 {
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (cudaMemcpyFromSymbol(out8, wb_phase_clk, sizeof(z)) != cudaSuccess) return WB_ECUDA;
+    unsigned long long z[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out12, wb_phase_clk, sizeof(z)) != cudaSuccess) return WB_ECUDA;
     if (cudaMemcpyToSymbol(wb_phase_clk, z, sizeof(z)) != cudaSuccess) return WB_ECUDA;
     return WB_OK;
 }

@@ -362,7 +362,7 @@ __device__ __forceinline__ float wb_b3_chain_generic(const float2 *q_, const flo
 
 #ifdef WB_PHASE_CLK
 /* debug build only (make dbg): cycles per phase summed over all CTAs and frames, read with wb_debug_phase_clk */
-__device__ unsigned long long wb_phase_clk[8];
+__device__ unsigned long long wb_phase_clk[12];
 #define WB_CLK(I) do { if (tid == 0) { const unsigned now_ = (unsigned)clock(); atomicAdd(&wb_phase_clk[I], (unsigned long long)(now_ - clk_prev)); clk_prev = now_; } } while (0)
 #else
 #define WB_CLK(I) do { } while (0)
@@ -712,6 +712,10 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
            warp never touch samples another warp still has to read.) */
         float2 ph_end = make_float2(0.0f, 0.0f);
         bool ph_store = false;
+#ifdef WB_PHASE_CLK
+        const unsigned bq0 = (unsigned)clock();
+        unsigned bq1 = bq0, bq2 = bq0, bq3 = bq0;
+#endif
         if (warp < p.b1_w) {
             const int m = lane / spb, s = lane - m * spb;
             const bool mine = lane < M * spb && (sc[min(s, spb - 1)].flags & 1);
@@ -733,6 +737,10 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 float2 *dst = (m == 0) ? Xs + (nst - nold) + sdl : Xs + XLEN + (m - 1) * ylen;
                 const int nold_hi = 2 * TS + TS / 2;          /* >= every possible nold */
                 const int seg0 = p.b1_seg[warp], seg1 = p.b1_seg[warp + 1];
+#ifdef WB_PHASE_CLK
+                asm volatile("" :: "f"(ph.x), "f"(d.x), "f"(dnew.x));
+                bq1 = (unsigned)clock();
+#endif
                 /* old -> new samples: comp_normalize + this frame's tone, reference src/fsk.c:787-788 */
 #define WB_B1_SWITCH()                                                                                  \
                 do {                                                                                    \
@@ -774,6 +782,10 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                             ph = wb_cmul2p(ph, d);
                         }
                     }
+#ifdef WB_PHASE_CLK
+                    asm volatile("" :: "f"(ph.x));
+                    bq2 = (unsigned)clock();
+#endif
 #pragma unroll 1
                     for (; n + 32 <= seg0; n += 32) {        /* long bodies: the loop's back edge costs the chain a bubble */
 #pragma unroll
@@ -787,6 +799,15 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
 #pragma unroll 1
                     for (; n < seg0; n++) ph = wb_cmul2p(ph, d);
                 }
+#ifdef WB_PHASE_CLK
+                asm volatile("" :: "f"(ph.x));
+                bq3 = (unsigned)clock();
+                if (lane == 0 && warp == p.b1_w - 1) {
+                    atomicAdd(&wb_phase_clk[4], (unsigned long long)(bq1 - bq0));
+                    atomicAdd(&wb_phase_clk[5], (unsigned long long)(bq2 - bq1));
+                    atomicAdd(&wb_phase_clk[7], (unsigned long long)(bq3 - bq2));
+                }
+#endif
                 /* batches of eight steps: all eight samples are loaded before the (in-place, swizzled) stores */
                 int n0 = seg0;
                 /* (a) the batches that can contain the switch */
@@ -837,6 +858,10 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
                 ph_end = ph;
                 ph_store = warp == p.b1_w - 1;
             }
+#ifdef WB_PHASE_CLK
+            asm volatile("" :: "f"(ph_end.x));
+            if (lane == 0) atomicAdd(&wb_phase_clk[8 + warp], (unsigned long long)((unsigned)clock() - bq0));
+#endif
         }
         __syncthreads();
         WB_CLK(1);
