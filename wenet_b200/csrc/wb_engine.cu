@@ -528,6 +528,21 @@ extern "C" int wb_create(const wb_config *cfg, wb_engine **out)
                 if (acc == nsteps) { W = j + 1; break; }
             }
             e->fp.b1_w = W;
+            /* experiments: explicit segment ends, e.g. WB_FSK_B1SEG=160,272,352 (multiples of 8, ascending, < nsteps) */
+            if (const char *sg = getenv("WB_FSK_B1SEG")) {
+                int w = 0, prev = 0;
+                bool ok = true;
+                while (*sg && w < WB_MAX_B1W - 1) {
+                    char *end = nullptr;
+                    const long v = strtol(sg, &end, 10);
+                    if (end == sg) break;
+                    if (v <= prev || v >= nsteps || v % 8) { ok = false; break; }
+                    e->fp.b1_seg[++w] = (int)v; prev = (int)v;
+                    sg = (*end == ',') ? end + 1 : end;
+                }
+                if (ok && w + 1 <= spb) { e->fp.b1_seg[w + 1] = nsteps; e->fp.b1_w = w + 1; }
+                else { wb_destroy(e); return wb_fail(WB_EINVAL, "WB_FSK_B1SEG: ascending multiples of 8 below the frame's step count, at most one segment per stream of a CTA"); }
+            }
         }
         e->fsk_smem = smem_for(spb);
         const bool cf32 = e->fp.in_fmt == WB_FMT_CF32, blk = e->fp.step == 1;
