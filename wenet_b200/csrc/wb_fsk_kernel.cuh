@@ -487,9 +487,10 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     unsigned clk_prev = (unsigned)clock();
 #endif
     for (;;) {
+        /* no CTA barrier between C and the next frame's A: both touch only the warp's own stream.  Whether any stream
+           still has a frame to do is voted at the barrier that ends A (a stream that is done stays done). */
         const bool active = have && (pos + (unsigned)nin <= fill) && (n_out + (unsigned)NBITS <= a.sd_cap);
-        if (!__syncthreads_or(active)) break;
-        WB_CLK(6);      /* C + loop barrier */
+        WB_CLK(6);      /* C (thread 0's own) */
         const unsigned pos_next = pos + nin;
         const int dlt = CF32 ? ((warp + nst + (int)pos) & 1) : 0;     /* this frame's samples start at X[nst + dlt] */
         const int xo = nst - (NMEM - nin) + dlt;   /* X index of the first mixer sample */
@@ -699,7 +700,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
         } else if (lane == 0) {
             sc[warp].flags = 0;
         }
-        __syncthreads();
+        if (!__syncthreads_or(active)) break;
         WB_CLK(0);
 
         /* ========== B1: warps 0..W-1, lane = (tone, stream): oscillator + down-mix ========== */
