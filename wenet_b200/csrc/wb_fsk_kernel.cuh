@@ -483,6 +483,7 @@ wb_fsk_kernel(wb_fsk_params p, wb_fsk_args a)
     const float omt = __fsub_rn(1.0f, p.tc);
     constexpr bool blocked = BLK;          /* P == Ts: the configuration every Wenet script uses */
 
+    __syncthreads();                       /* the twiddle table above is filled by all threads and read by every warp's first A */
 #ifdef WB_PHASE_CLK
     unsigned clk_prev = (unsigned)clock();
 #endif
