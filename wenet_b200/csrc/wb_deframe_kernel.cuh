@@ -21,7 +21,7 @@
 #include "wb_internal.h"
 
 #ifndef WB_DEFRAME_NF
-#define WB_DEFRAME_NF 12
+#define WB_DEFRAME_NF 16
 #endif
 
 __global__ void __launch_bounds__(128)
@@ -51,21 +51,28 @@ wb_deframe_kernel(wb_deframe_params p, wb_stream_state *state, wb_cursor *cursor
         }
     }
     /* WB_DEFRAME_NF x 32 symbols are fetched per round (that many independent loads per lane in flight: the scan is a
-       chain of L2 round trips otherwise), then examined 32 at a time; a hit restarts the round at the jump target */
+       chain of L2 round trips otherwise), then examined 32 at a time; a hit restarts the round at the jump target.
+       The round after this one is fetched before this one is examined: a stream without packets -- the slowest kind,
+       every symbol is looked at -- then never waits for memory; after a hit the fetched round is dropped. */
+    float va[WB_DEFRAME_NF], vb[WB_DEFRAME_NF];
+#define WB_DEFRAME_FETCH(V, T0)                                                                         \
+    do {                                                                                                \
+        _Pragma("unroll") for (int k = 0; k < WB_DEFRAME_NF; k++) {                                     \
+            const int idx = (T0) + 32 * k + lane;                                                       \
+            V[k] = (idx < n_new) ? row[WB_CARRY_CAP + idx] : 0.0f;                                      \
+        }                                                                                               \
+    } while (0)
+    if (t < n_new) WB_DEFRAME_FETCH(va, t);
     while (t < n_new) {
-        float v4[WB_DEFRAME_NF];
-#pragma unroll
-        for (int k = 0; k < WB_DEFRAME_NF; k++) {
-            const int idx = t + 32 * k + lane;
-            v4[k] = (idx < n_new) ? row[WB_CARRY_CAP + idx] : 0.0f;
-        }
+        const int t_next = t + 32 * WB_DEFRAME_NF;
+        if (t_next < n_new) WB_DEFRAME_FETCH(vb, t_next);
         bool jumped = false;
 #pragma unroll
         for (int k = 0; k < WB_DEFRAME_NF; k++) {
             if (jumped || t >= n_new) break;
             const int idx = t + lane;
             const bool valid = idx < n_new;
-            const float v = v4[k];
+            const float v = va[k];
             unsigned nb = __ballot_sync(0xffffffffu, valid && (v < 0.0f));
             /* window after symbol t+lane: symbols t..t+lane appended, newest in bit 0 */
             unsigned long long Wj = (W << (lane + 1)) | (unsigned long long)(__brev(nb) >> (31 - lane));
@@ -90,7 +97,15 @@ wb_deframe_kernel(wb_deframe_params p, wb_stream_state *state, wb_cursor *cursor
                 t += nvalid;
             }
         }
+        if (t >= n_new) break;
+        if (jumped) {
+            WB_DEFRAME_FETCH(va, t);
+        } else {                                         /* t == t_next: the round fetched ahead is the next one */
+#pragma unroll
+            for (int k = 0; k < WB_DEFRAME_NF; k++) va[k] = vb[k];
+        }
     }
+#undef WB_DEFRAME_FETCH
     if (lane == 0) {
         st.window = W;
         st.collecting = collecting;
