@@ -102,3 +102,19 @@ def test_c_example_builds_and_fails_loudly_without_a_gpu(tmp_path):
     src.write_bytes(bytes(4096))
     r = subprocess.run([exe, str(src), str(tmp_path / "out.bin")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 2 and b"no CPU fallback" in r.stderr
+
+
+def test_no_contracted_packed_arithmetic_in_the_library():
+    """The kernels use mul.rn.f32x2 / add.rn.f32x2 where that is the same floats as the reference's separate products and
+    sums.  ptxas 12.9 contracts a packed product that feeds a packed sum into ONE FFMA2 -- a single rounding -- even for
+    the explicit .rn forms and with --fmad false (found in round 2: an oscillator step written as two packed products +
+    one packed sum came out as FMUL2 + FFMA2).  The shipped code never feeds a packed product into a packed sum, so the
+    library must not contain a single FFMA2; this catches a build where an edit re-opened the door."""
+    import shutil
+    import subprocess
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "wenet_b200", "libwenet_b200.so")
+    if not os.path.exists(so) or shutil.which("cuobjdump") is None:
+        pytest.skip("no built library or no cuobjdump here")
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, timeout=600).stdout
+    assert sass.count("FMUL2") > 1000 and sass.count("FADD2") > 100      # the packed forms are there ...
+    assert sass.count("FFMA2") == 0                                       # ... and none of them was contracted
