@@ -19,9 +19,11 @@
  *   CTA = spb streams (runtime; 14 for 2-FSK at Ts = 8 so that two CTAs = 28 streams fit one SM and
  *   4096 streams are all resident on 148 SMs), one "stream warp" per stream, frames in lock step.
  *
- *   A  (stream warps)  the frame arrives by cp.async (issued at the end of the previous frame; every
- *                      frame is also prefetched into L2 one frame ahead, so HBM latency is off the
- *                      critical path and no registers are tied up); window + 256-point FFT in the
+ *   A  (stream warps)  the frame arrives as ONE TMA bulk copy per stream (cf32: cp.async.bulk + an mbarrier
+ *                      counting the bytes, issued by lane 0 at the end of the previous frame; the integer
+ *                      formats are fetched and converted by the warp; every frame is also prefetched into
+ *                      L2 one frame ahead, so HBM latency is off the critical path and no registers are
+ *                      tied up); window + 256-point FFT in the
  *                      reference's butterfly order (leaf level fused with the window, top level with
  *                      |X|^2 and the IIR; bank-conflict-free swizzled work buffer), spectrum IIR in
  *                      registers, warp-argmax peak picking.
@@ -38,7 +40,10 @@
  *   C  (stream warps)  every lane recomputes the frame's scalars from t_c (atan2 timing estimate,
  *                      ppm, next nin, resampling offsets); lanes = symbols: linear-interpolated
  *                      resampling and soft decisions, 48 (96) floats per frame written coalesced;
- *                      next frame's cp.async.
+ *                      next frame's fetch.
+ *
+ * Four CTA barriers per frame: A|B1, B1|B2, B2|B3, B3|C.  C and the next frame's A are work of the stream's own
+ * warp on the stream's own memory, so nothing separates them; the vote "any stream left?" rides on A|B1.
  *
  * The sequential phases cost a few warps' issue slots for ALL streams of the CTA (every lane carries
  * a different dependent chain); while one CTA of an SM is in B1/B3 the other one runs A/B2/C.
