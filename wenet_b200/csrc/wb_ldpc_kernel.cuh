@@ -88,6 +88,24 @@ __device__ __forceinline__ void wb_llr_stats_load8(const float *row, int k, cons
     }
 }
 
+/* a / b for many a and one b: with y = RN(1 / b) (one real division per codeword),
+       q0 = RN(a y);  q1 = RN(q0 + (a - b q0) y);  q = RN(q1 + (a - b q1) y)
+   is the correctly rounded quotient, i.e. bit for bit the IEEE division the reference executes: q1 is within 1/2 ulp +
+   2^-105 of a / b (a y is off by at most 2^-52 relatively, the first correction removes that to second order), the
+   residual a - b q1 is then exact in one fma, and a faithful quotient corrected once more with a correctly rounded
+   reciprocal rounds correctly (Markstein, "IA-64 and Elementary Functions", the final step of Itanium's division).
+   Checked against a / b on 3.2e10 random pairs (a any float, b plausible means, extreme exponents, significands of all
+   ones and of few bits, scaled sums of floats): no difference.  5 double-precision instructions instead of the ~13 of
+   the division routine, per element of the second pass.  Only for a b whose reciprocal is a normal number (else the
+   plain division); a = -0 gives +0 instead of -0, which the sums that follow cannot see (they start at +0). */
+__device__ __forceinline__ double wb_quot(double a, double b, double y, bool fast)
+{
+    if (!fast) return a / b;
+    const double q0 = __dmul_rn(a, y);
+    const double q1 = __fma_rn(__fma_rn(-b, q0, a), y, q0);
+    return __fma_rn(__fma_rn(-b, q1, a), y, q1);
+}
+
 template <int FRAMING>
 __device__ __forceinline__ double wb_llr_stats_row(const float *row, const uint8_t *scramble)
 {
@@ -107,13 +125,15 @@ __device__ __forceinline__ double wb_llr_stats_row(const float *row, const uint8
         for (int j = 0; j < TAIL; j++) sum += fabs(v[j]);
     }
     const double mean = sum / (double)n;
+    const double rcp = 1.0 / mean;
+    const bool fast = mean > 1e-290 && mean < 1e290;        /* false for 0, NaN, infinity too */
     sum = 0.0;
 #pragma unroll 2
     for (int k = 0; k < NB; k++) {
         double v[8], x[8];
         wb_llr_stats_load8<FRAMING>(row, k, scramble, v);
 #pragma unroll
-        for (int j = 0; j < 8; j++) x[j] = v[j] / mean - (double)((v[j] > 0.0) - (v[j] < 0.0));
+        for (int j = 0; j < 8; j++) x[j] = wb_quot(v[j], mean, rcp, fast) - (double)((v[j] > 0.0) - (v[j] < 0.0));
 #pragma unroll
         for (int j = 0; j < 8; j++) { sum += x[j]; sumsq += x[j] * x[j]; }
     }
@@ -121,7 +141,7 @@ __device__ __forceinline__ double wb_llr_stats_row(const float *row, const uint8
         double v[8], x[8];
         wb_llr_stats_load8<FRAMING>(row, NB, scramble, v);
 #pragma unroll
-        for (int j = 0; j < TAIL; j++) x[j] = v[j] / mean - (double)((v[j] > 0.0) - (v[j] < 0.0));
+        for (int j = 0; j < TAIL; j++) x[j] = wb_quot(v[j], mean, rcp, fast) - (double)((v[j] > 0.0) - (v[j] < 0.0));
 #pragma unroll
         for (int j = 0; j < TAIL; j++) { sum += x[j]; sumsq += x[j] * x[j]; }
     }
